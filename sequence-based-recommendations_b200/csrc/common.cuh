@@ -1,0 +1,196 @@
+// common.cuh -- shared declarations of libsbr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/sbr_b200.h"
+
+#define SBR_WARP 32
+#define SBR_NSM 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- error plumbing -------------------------------------------------------------------------
+struct sbr_model;
+void sbr_set_error(sbr_model* m, int code, const char* fmt, ...);
+
+#define CU_TRY(m, expr)                                                                 \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      sbr_set_error((m), SBR_E_CUDA, "%s failed: %s (%s:%d)", #expr,                    \
+                    cudaGetErrorString(e__), __FILE__, __LINE__);                       \
+      return SBR_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
+#define KERNEL_CHECK(m)                                                                 \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) {                                                           \
+      sbr_set_error((m), SBR_E_CUDA, "kernel launch failed: %s (%s:%d)",                \
+                    cudaGetErrorString(e__), __FILE__, __LINE__);                       \
+      return SBR_E_CUDA;                                                                \
+    }                                                                                   \
+    (m)->launches++;                                                                    \
+  } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- model description ----------------------------------------------------------------------
+struct LayerDesc {
+  int H = 0;           // hidden units
+  int G = 0;           // stacked gate blocks: LSTM 4 [in,forget,cell,out], GRU 3 [reset,update,hidden], Vanilla 1
+  int I = 0;           // dense input width; 0 = id gather-sum layer (layer 0 without embedding)
+  int in_rows = 0;     // rows of W_in (n_items + n_extra_ids for the gather layer, I otherwise)
+  int64_t W_in = 0;    // arena offsets (floats)            [in_rows, G*H]
+  int64_t W_hid = 0;   //                                   [H, G*H]
+  int64_t b = 0;       //                                   [G*H]
+  int64_t peep = 0;    // LSTM only: w_ci, w_cf, w_co       [3, H]
+  int64_t c_init = 0;  // LSTM only                         [H]
+  int64_t h_init = 0;  //                                   [H]
+  // per-layer workspaces (time-major, row = t*B + b)
+  float* Xg = nullptr;    // [T*B, G*H]  input pre-activations (gather / input GEMM + bias)
+  float* act = nullptr;   // [T*B, 4*H]  saved activations (LSTM i,f,g,o | GRU r,u,cand,a_c)
+  float* hs = nullptr;    // [(T+1)*B, H] hs[0] = init broadcast, hs[t+1] = state after step t
+  float* cs = nullptr;    // LSTM: same for the cell state
+  float* dXg = nullptr;   // [T*B, G*H]  gradient wrt Xg (zero on masked steps)
+  float* dac = nullptr;   // GRU: [T*B, H] gradient wrt the candidate's hidden pre-activation (da_c)
+  float* dhs = nullptr;   // [T*B, H]   gradient arriving from the layer above (nullptr for the top layer)
+};
+
+struct ParamView {       // one entry of the reference checkpoint list
+  std::string name;
+  int ndim = 1;
+  int64_t shape[4] = {1, 1, 1, 1};
+  int64_t off = 0;       // arena offset of element (0,0)
+  int64_t rows = 1, cols = 1;
+  int64_t ld = 1;        // arena row stride
+  bool transposed = false;  // arena holds the transpose ([cols, rows] with stride ld)
+};
+
+struct BatchSlot {       // device-resident inputs of one mini-batch
+  int32_t* X = nullptr;       // [B, T, K]
+  int32_t* len = nullptr;     // [B]
+  int32_t* Y = nullptr;       // [n_all] targets (CCE: B)
+  float* pop = nullptr;       // [B]
+  int B = 0, t_max = 0, n_all = 0, row_offset = 0;
+};
+
+struct sbr_model {
+  sbr_config cfg{};
+  int dev = 0;
+  int n_sm = SBR_NSM;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int err_code = 0;
+  int64_t launches = 0;
+
+  // geometry
+  int B = 0, T = 0, K = 1, N = 0, n_in = 0, E = 0, L = 0, H_last = 0;
+  int global_batch = 0;
+  std::vector<LayerDesc> layers;
+  std::vector<ParamView> views;
+
+  // flat arenas (one allocation each => one all-reduce, one fused optimizer launch)
+  int64_t P = 0;           // number of parameters
+  int64_t P_pad = 0;       // arena length (16B-aligned blocks + cost slot)
+  int64_t cost_slot = 0;   // index of the cost scalar inside the gradient arena
+  float* params = nullptr;
+  float* grads = nullptr;
+  float* opt_a = nullptr;
+  float* opt_b = nullptr;
+  int64_t opt_t = 0;
+  int64_t emb_W = 0, out_WT = 0, out_b = 0;   // arena offsets; out_WT is [N, H_last] (item-major)
+
+  // workspaces
+  std::vector<BatchSlot> slots;
+  float* emb_out = nullptr;   // [T*B, K*E]
+  float* demb = nullptr;
+  float* h_last = nullptr;    // [B, H_last]
+  float* dh_last = nullptr;   // [B, H_last]
+  float* logits = nullptr;    // [B, max(N, n_all+S)]
+  float* row_loss = nullptr;  // [B]
+  float* WhidT = nullptr;     // scratch transpose of the largest W_hid (global-memory fallback of the bwd kernel)
+  // margin / sampled
+  float* mY = nullptr;        // [B, N]
+  float* mW = nullptr;        // [B, N]
+  int32_t* cells = nullptr;   // [n_all + S]
+  float* Wc = nullptr;        // [n_all+S, H_last] gathered output rows
+  float* dWc = nullptr;
+  float* bc = nullptr;        // gathered output bias [n_all+S]
+  int32_t* tgt_off = nullptr; // ragged margin targets
+  int32_t* tgt_ids = nullptr;
+  float* w_neg = nullptr;
+  float* def_tgt = nullptr;
+  int tgt_cap = 0;
+  // top-k
+  int32_t* excl_off = nullptr;
+  int32_t* excl_ids = nullptr;
+  int excl_cap = 0;
+  int32_t* topk_ids = nullptr;
+  // host staging (pinned)
+  int32_t* h_len = nullptr;
+  float* h_cost = nullptr;
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+
+  // nccl
+  void* nccl_comm = nullptr;
+
+  // profiling
+  bool profiling = false;
+  bool skip_update = false;
+  cudaEvent_t ev[SBR_N_STAGES + 1] = {};
+  float stage_ms[SBR_N_STAGES] = {};
+};
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------
+// gather_scatter.cu
+int launch_gather_rows(sbr_model* m, const int32_t* X, const int32_t* len, const float* W, const float* bias,
+                       float* out, int B, int T, int K, int ncols, int t_max, int n_rows_table);
+int launch_scatter_add_rows(sbr_model* m, const int32_t* X, const int32_t* len, const float* dOut, float* dW,
+                            int B, int T, int K, int ncols, int t_max);
+int launch_colsum(sbr_model* m, const float* A, int rows, int cols, int ld, float* out /* += */);
+int launch_gather_table_rows(sbr_model* m, const float* table, const float* bias, const int32_t* ids, int n_ids,
+                             int ncols, float* out_rows, float* out_bias);
+int launch_scatter_table_rows(sbr_model* m, const float* rows, const float* brow, const int32_t* ids, int n_ids,
+                              int ncols, float* table_grad, float* bias_grad);
+int launch_transpose(sbr_model* m, const float* in, int rows, int cols, int ld_in, float* out);
+int launch_embed_gather(sbr_model* m, const int32_t* X, const int32_t* len, const float* table, float* out,
+                        int B, int T, int K, int E, int t_max);
+int launch_embed_scatter(sbr_model* m, const int32_t* X, const int32_t* len, const float* dOut, float* dTable,
+                         int B, int T, int K, int E, int t_max);
+
+// rnn_cluster.cu
+int launch_rnn_forward(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last);
+int launch_rnn_backward(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max,
+                        const float* dh_last /* top layer, else nullptr */);
+
+// gemm.cu : C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (row-major, beta in {0,1})
+int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
+                int ldb, float* C, int ldc, float alpha, float beta);
+
+// loss.cu
+int launch_cce(sbr_model* m, float* logits, int ld, const float* bias, const int32_t* Y, const float* pop, int B,
+               int N, float inv_global_batch, float* row_loss);
+int launch_softmax_rows(sbr_model* m, float* logits, int ld, const float* bias, int B, int N);
+int launch_add_bias_rows(sbr_model* m, float* logits, int ld, const float* bias, int B, int N);
+int launch_sampling_loss(sbr_model* m, int loss, bool tanh_out, float* A, int ld, const float* bias_cells,
+                         const float* pop, int B, int n_all, int row_offset, int S, float inv_global_batch,
+                         float* row_loss);
+int launch_margin_loss(sbr_model* m, int loss, float* pred, int ld, const float* bias, const float* Y,
+                       const float* W, int B, int N, float inv_global_batch, float* row_loss);
+int launch_margin_fill(sbr_model* m, float* Y, float* W, const int32_t* X, const int32_t* len, const int32_t* toff,
+                       const int32_t* tids, const float* w_neg, const float* def_tgt, int exclude_seen, int B,
+                       int T, int K, int N);
+int launch_bias_reg(sbr_model* m, const float* b, float* db, int N, float reg, float* cost_acc);
+int launch_reduce_cost(sbr_model* m, const float* row_loss, int B, float* cost_acc);
+int launch_topk(sbr_model* m, float* scores, int ld, int B, int N, const int32_t* excl_off, const int32_t* excl_ids,
+                int k, int neg_inf, int32_t* ids_out);
+
+// optim.cu
+int launch_optimizer(sbr_model* m);

@@ -1,0 +1,300 @@
+// gather_scatter.cu -- stage 1 of the hot path and its transpose.
+//
+//   gather : Xg[t*B+b, :] = sum_k W_in[X[b,t,k], :] + bias        (valid steps only)
+//            reference: W_in_stacked[input, :].sum(axis=-2) + b_stacked
+//            (neural_networks/sparse_lstm.py:368, :755, :1111)
+//   scatter: dW_in[X[b,t,k], :] += dXg[t*B+b, :]                   (duplicates accumulate)
+//            reference: gradient of the AdvancedSubtensor1 above (theano.grad, rnn_base.py:183)
+//
+// Both are HBM-bound row copies.  Rows are G*H floats (0.6-8 KB) so one warp moves one row with
+// 128-bit accesses; the grid is a multiple of the SM count.  The scatter is duplicate-heavy: a
+// reference mini-batch is B nested prefixes of ONE user's sequence (rnn_base.py:396-415), so at a
+// given timestep up to B rows carry the same item id.  The warp therefore groups its 32
+// consecutive (t, b) entries by id with match.any and issues ONE red.global.add per distinct id
+// (warp-aggregated atomics) instead of 32.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// one warp per (t, b) row; VEC4 requires ncols % 4 == 0 and 16B-aligned bases
+template <bool VEC4>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ len,
+                                                           const float* __restrict__ W, const float* __restrict__ bias,
+                                                           float* __restrict__ out, int B, int T, int K, int ncols,
+                                                           int n_rows, int n_table) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * warps_per_block) {
+    const int t = row / B, b = row - t * B;
+    if (t >= len[b]) continue;  // padded step: never read downstream
+    const int32_t* ids = X + ((int64_t)b * T + t) * K;
+    float* o = out + (int64_t)row * ncols;
+    if (VEC4) {
+      for (int c = lane * 4; c < ncols; c += 128) {
+        float4 acc = ld4(bias + c);
+        for (int k = 0; k < K; ++k) {
+          int id = __ldg(ids + k);
+          id = min(max(id, 0), n_table - 1);
+          float4 w = ld4(W + (int64_t)id * ncols + c);
+          acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+        }
+        st4(o + c, acc);
+      }
+    } else {
+      for (int c = lane; c < ncols; c += 32) {
+        float acc = bias[c];
+        for (int k = 0; k < K; ++k) {
+          int id = __ldg(ids + k);
+          id = min(max(id, 0), n_table - 1);
+          acc += W[(int64_t)id * ncols + c];
+        }
+        o[c] = acc;
+      }
+    }
+  }
+}
+
+// Warp-aggregated scatter-add.  A warp owns 32 consecutive time-major entries e = t*B + b (same t,
+// consecutive b => same id under the nested-prefix batch layout).
+template <bool VEC4>
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int32_t* __restrict__ X,
+                                                                const int32_t* __restrict__ len,
+                                                                const float* __restrict__ dOut, float* __restrict__ dW,
+                                                                int B, int T, int K, int ncols, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int n_groups = (n_rows + 31) / 32;
+  for (int grp = blockIdx.x * warps_per_block + (threadIdx.x >> 5); grp < n_groups; grp += gridDim.x * warps_per_block) {
+    const int e = grp * 32 + lane;
+    int t = 0, b = 0;
+    bool valid = e < n_rows;
+    if (valid) {
+      t = e / B;
+      b = e - t * B;
+      valid = t < len[b];
+    }
+    for (int k = 0; k < K; ++k) {
+      // invalid lanes get distinct negative keys so they never join a group
+      const int id = valid ? X[((int64_t)b * T + t) * K + k] : -1 - lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, id);
+      const bool leader = valid && (__ffs(peers) - 1 == lane);
+      unsigned leaders = __ballot_sync(0xffffffffu, leader);
+      while (leaders) {
+        const int L = __ffs(leaders) - 1;
+        leaders &= leaders - 1;
+        const unsigned members = __shfl_sync(0xffffffffu, peers, L);
+        const int rid = __shfl_sync(0xffffffffu, id, L);
+        float* dst = dW + (int64_t)rid * ncols;
+        const float* src0 = dOut + (int64_t)grp * 32 * ncols;
+        if (VEC4) {
+          for (int c = lane * 4; c < ncols; c += 128) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned mm = members;
+            while (mm) {
+              const int mlane = __ffs(mm) - 1;
+              mm &= mm - 1;
+              float4 v = ld4(src0 + (int64_t)mlane * ncols + c);
+              s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            atomicAdd(dst + c, s.x);
+            atomicAdd(dst + c + 1, s.y);
+            atomicAdd(dst + c + 2, s.z);
+            atomicAdd(dst + c + 3, s.w);
+          }
+        } else {
+          for (int c = lane; c < ncols; c += 32) {
+            float s = 0.f;
+            unsigned mm = members;
+            while (mm) {
+              const int mlane = __ffs(mm) - 1;
+              mm &= mm - 1;
+              s += src0[(int64_t)mlane * ncols + c];
+            }
+            atomicAdd(dst + c, s);
+          }
+        }
+      }
+    }
+  }
+}
+
+// out[c] += sum_r A[r*ld + c]   (A is zero on masked rows, so no mask is needed)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int rows, int cols, int ld,
+                                                      int rows_per_block, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += A[(int64_t)r * ld + c];
+    s1 += A[(int64_t)(r + 1) * ld + c];
+    s2 += A[(int64_t)(r + 2) * ld + c];
+    s3 += A[(int64_t)(r + 3) * ld + c];
+  }
+  for (; r < r1; ++r) s0 += A[(int64_t)r * ld + c];
+  atomicAdd(out + c, (s0 + s1) + (s2 + s3));
+}
+
+// rows of an item-major table (output embeddings): out_rows[i,:] = table[ids[i],:], out_bias[i] = bias[ids[i]]
+__global__ void __launch_bounds__(256) gather_table_rows_kernel(const float* __restrict__ table,
+                                                                 const float* __restrict__ bias,
+                                                                 const int32_t* __restrict__ ids, int n_ids, int ncols,
+                                                                 float* __restrict__ out_rows,
+                                                                 float* __restrict__ out_bias) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_ids) return;
+  const int id = ids[w];
+  for (int c = lane; c < ncols; c += 32) out_rows[(int64_t)w * ncols + c] = table[(int64_t)id * ncols + c];
+  if (lane == 0 && out_bias) out_bias[w] = bias[id];
+}
+
+__global__ void __launch_bounds__(256) scatter_table_rows_kernel(const float* __restrict__ rows,
+                                                                  const float* __restrict__ brow,
+                                                                  const int32_t* __restrict__ ids, int n_ids,
+                                                                  int ncols, float* __restrict__ table_grad,
+                                                                  float* __restrict__ bias_grad) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_ids) return;
+  const int id = ids[w];
+  for (int c = lane; c < ncols; c += 32) atomicAdd(table_grad + (int64_t)id * ncols + c, rows[(int64_t)w * ncols + c]);
+  if (lane == 0 && bias_grad) atomicAdd(bias_grad + id, brow[w]);
+}
+
+// out[c*rows + r] = in[r*ld_in + c]
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(int64_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// EmbeddingLayer (recurrent_layers.py:47-50): out[t*B+b, k*E + e] = table[X[b,t,k], e]
+__global__ void __launch_bounds__(256) embed_gather_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ len,
+                                                            const float* __restrict__ table, float* __restrict__ out,
+                                                            int B, int T, int K, int E, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int t = row / B, b = row - t * B;
+  const bool valid = t < len[b];
+  for (int k = 0; k < K; ++k) {
+    const int id = valid ? X[((int64_t)b * T + t) * K + k] : 0;
+    for (int e = lane; e < E; e += 32)
+      out[(int64_t)row * K * E + k * E + e] = valid ? table[(int64_t)id * E + e] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) embed_scatter_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ len,
+                                                             const float* __restrict__ dOut, float* __restrict__ dTable,
+                                                             int B, int T, int K, int E, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int t = row / B, b = row - t * B;
+  if (t >= len[b]) return;
+  for (int k = 0; k < K; ++k) {
+    const int id = X[((int64_t)b * T + t) * K + k];
+    for (int e = lane; e < E; e += 32) atomicAdd(dTable + (int64_t)id * E + e, dOut[(int64_t)row * K * E + k * E + e]);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int launch_gather_rows(sbr_model* m, const int32_t* X, const int32_t* len, const float* W, const float* bias,
+                       float* out, int B, int T, int K, int ncols, int t_max, int n_rows_table) {
+  const int n_rows = t_max * B;
+  if (n_rows == 0) return 0;
+  const int wpb = 8;
+  int grid = cdiv(n_rows, wpb);
+  grid = std::min(grid, m->n_sm * 16);
+  const bool v4 = (ncols % 4 == 0) && aligned16(W) && aligned16(bias) && aligned16(out);
+  if (v4)
+    gather_rows_kernel<true><<<grid, wpb * 32, 0, m->stream>>>(X, len, W, bias, out, B, T, K, ncols, n_rows, n_rows_table);
+  else
+    gather_rows_kernel<false><<<grid, wpb * 32, 0, m->stream>>>(X, len, W, bias, out, B, T, K, ncols, n_rows, n_rows_table);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_scatter_add_rows(sbr_model* m, const int32_t* X, const int32_t* len, const float* dOut, float* dW,
+                            int B, int T, int K, int ncols, int t_max) {
+  const int n_rows = t_max * B;
+  if (n_rows == 0) return 0;
+  const int wpb = 8;
+  int grid = cdiv(cdiv(n_rows, 32), wpb);
+  grid = std::min(grid, m->n_sm * 16);
+  const bool v4 = (ncols % 4 == 0) && aligned16(dOut) && aligned16(dW);
+  if (v4)
+    scatter_add_rows_kernel<true><<<grid, wpb * 32, 0, m->stream>>>(X, len, dOut, dW, B, T, K, ncols, n_rows);
+  else
+    scatter_add_rows_kernel<false><<<grid, wpb * 32, 0, m->stream>>>(X, len, dOut, dW, B, T, K, ncols, n_rows);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_colsum(sbr_model* m, const float* A, int rows, int cols, int ld, float* out) {
+  if (rows == 0 || cols == 0) return 0;
+  const int gx = cdiv(cols, 256);
+  int gy = std::max(1, std::min(cdiv(rows, 64), (m->n_sm * 4) / gx));
+  const int rpb = cdiv(rows, gy);
+  gy = cdiv(rows, rpb);
+  colsum_kernel<<<dim3(gx, gy), 256, 0, m->stream>>>(A, rows, cols, ld, rpb, out);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_gather_table_rows(sbr_model* m, const float* table, const float* bias, const int32_t* ids, int n_ids,
+                             int ncols, float* out_rows, float* out_bias) {
+  if (n_ids == 0) return 0;
+  gather_table_rows_kernel<<<cdiv(n_ids, 8), 256, 0, m->stream>>>(table, bias, ids, n_ids, ncols, out_rows, out_bias);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_scatter_table_rows(sbr_model* m, const float* rows, const float* brow, const int32_t* ids, int n_ids,
+                              int ncols, float* table_grad, float* bias_grad) {
+  if (n_ids == 0) return 0;
+  scatter_table_rows_kernel<<<cdiv(n_ids, 8), 256, 0, m->stream>>>(rows, brow, ids, n_ids, ncols, table_grad, bias_grad);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_transpose(sbr_model* m, const float* in, int rows, int cols, int ld_in, float* out) {
+  transpose_kernel<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), dim3(32, 8), 0, m->stream>>>(in, rows, cols, ld_in, out);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_embed_gather(sbr_model* m, const int32_t* X, const int32_t* len, const float* table, float* out,
+                        int B, int T, int K, int E, int t_max) {
+  const int n_rows = t_max * B;
+  if (n_rows == 0) return 0;
+  embed_gather_kernel<<<cdiv(n_rows, 8), 256, 0, m->stream>>>(X, len, table, out, B, T, K, E, n_rows);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_embed_scatter(sbr_model* m, const int32_t* X, const int32_t* len, const float* dOut, float* dTable,
+                         int B, int T, int K, int E, int t_max) {
+  const int n_rows = t_max * B;
+  if (n_rows == 0) return 0;
+  embed_scatter_kernel<<<cdiv(n_rows, 8), 256, 0, m->stream>>>(X, len, dOut, dTable, B, T, K, E, n_rows);
+  KERNEL_CHECK(m);
+  return 0;
+}

@@ -1,0 +1,154 @@
+// gemm.cu -- fp32 GEMM used by every non-recurrent GEMM-shaped stage of the path:
+//   output projection   logits[B,N]   = h_T[B,H] * W_out^T          (rnn_one_hot.py:65, rnn_margin.py:103)
+//   its two gradients   dW_out^T[N,H] = dlogits^T * h_T ; dh_T = dlogits * W_out^T
+//   layer>=1 / embedding input GEMM  Xg[T*B,G*H] = in[T*B,I] * W_in  (Lasagne precompute_input)
+//   BPTT weight gradient dW_hid[H,G*H] = sum_t h_{t-1}^T * dgates_t  (one K = T*B GEMM after the scan)
+//
+// C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, fp32 in / fp32 accumulate (SBR_MATH_FP32).
+// 128x128x8 CTA tile, 8x8 register micro-tile, register-staged global->shared prefetch; split-K
+// over gridDim.z (fp32 atomics) so that tall-K / small-MN problems still fill 148 SMs.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 8, PAD = 4;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                     const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                     int ldc, float alpha, int k_per_split, int accumulate) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      int mm, kk;
+      if (TA) { kk = idx / BM; mm = idx % BM; } else { mm = idx / BK; kk = idx % BK; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < k_end) v = TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+      ra[i] = v;
+      int nn, kb;
+      if (TB) { nn = idx / BK; kb = idx % BK; } else { kb = idx / BN; nn = idx % BN; }
+      const int gn = n0 + nn, gkb = k0 + kb;
+      float w = 0.f;
+      if (gn < N && gkb < k_end) w = TB ? B[(int64_t)gn * ldb + gkb] : B[(int64_t)gkb * ldb + gn];
+      rb[i] = w;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      int mm, kk;
+      if (TA) { kk = idx / BM; mm = idx % BM; } else { mm = idx / BK; kk = idx % BK; }
+      As[kk][mm] = ra[i];
+      int nn, kb;
+      if (TB) { nn = idx / BK; kb = idx % BK; } else { kb = idx / BN; nn = idx % BN; }
+      Bs[kb][nn] = rb[i];
+    }
+  };
+
+  if (k_begin < k_end) {
+    load_tiles(k_begin);
+    store_tiles();
+    __syncthreads();
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+      const bool more = k0 + BK < k_end;
+      if (more) load_tiles(k0 + BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+      if (more) {
+        store_tiles();
+        __syncthreads();
+      }
+    }
+  }
+
+  const bool atomic_out = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= N) continue;
+      float* c = C + (int64_t)gm * ldc + gn;
+      const float v = alpha * acc[i][j];
+      if (atomic_out) atomicAdd(c, v);
+      else if (accumulate) *c += v;
+      else *c = v;
+    }
+  }
+}
+
+__global__ void zero_matrix_kernel(float* C, int M, int N, int ldc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  C[(i / N) * ldc + (i % N)] = 0.f;
+}
+
+}  // namespace
+
+int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
+                int ldb, float* C, int ldc, float alpha, float beta) {
+  if (M <= 0 || N <= 0) return 0;
+  if (beta != 0.f && beta != 1.f) {
+    sbr_set_error(m, SBR_E_ARG, "gemm: beta must be 0 or 1");
+    return SBR_E_ARG;
+  }
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  int splits = 1;
+  if (K > 0) {
+    splits = std::max(1, std::min(cdiv(2 * m->n_sm, tiles), cdiv(K, 64)));
+    if (tiles >= m->n_sm) splits = 1;
+  }
+  int kps = K > 0 ? (int)round_up(cdiv(K, splits), BK) : BK;
+  splits = K > 0 ? cdiv(K, kps) : 1;
+  if (splits > 1 && beta == 0.f) {
+    if (ldc == N) {
+      cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), m->stream);
+      if (e != cudaSuccess) { sbr_set_error(m, SBR_E_CUDA, "memset: %s", cudaGetErrorString(e)); return SBR_E_CUDA; }
+    } else {
+      zero_matrix_kernel<<<cdiv((int64_t)M * N, 256), 256, 0, m->stream>>>(C, M, N, ldc);
+      KERNEL_CHECK(m);
+    }
+  }
+  const dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
+  const int accumulate = beta == 1.f ? 1 : 0;
+  if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
+  else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
+  else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
+  else sgemm_kernel<true, true><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
+  KERNEL_CHECK(m);
+  return 0;
+}
