@@ -151,11 +151,15 @@ SBR_API int sbr_topk(sbr_model* m, const int32_t* X, const float* mask, int B, c
              const int32_t* excl_ids, int k, int mode, int32_t* ids_out);
 
 /* ---- measurement ------------------------------------------------------------------------ */
-#define SBR_N_STAGES 8
-SBR_API const char* sbr_stage_name(int i);            /* "h2d","gather","rnn_fwd","output","rnn_bwd","scatter","allreduce","optimizer" */
+#define SBR_N_STAGES 9
+SBR_API const char* sbr_stage_name(int i);            /* "h2d","gather","rnn_fwd","output","rnn_bwd","wgrad","scatter","allreduce","optimizer" */
 SBR_API int sbr_set_profiling(sbr_model* m, int on);  /* record a cudaEvent pair around every stage */
 SBR_API int sbr_stage_times(sbr_model* m, float ms[SBR_N_STAGES]);   /* of the last profiled step   */
 SBR_API int64_t sbr_kernel_launches(const sbr_model* m);             /* kernels launched since create */
+/* device-side stopwatch on the handle's stream (cudaEvent pair): start synchronises the stream
+ * first, stop blocks until the stop event has completed and returns the elapsed milliseconds */
+SBR_API int sbr_timer_start(sbr_model* m);
+SBR_API int sbr_timer_stop(sbr_model* m, float* ms);
 
 #ifdef __cplusplus
 }

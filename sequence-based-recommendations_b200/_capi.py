@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libsbr_b200.so")
 
 SBR_MAX_LAYERS = 8
 SBR_NCCL_ID_BYTES = 128
-SBR_N_STAGES = 8
+SBR_N_STAGES = 9
 
 CELLS = {"LSTM": 0, "GRU": 1, "Vanilla": 2}
 LOSSES = {"CCE": 0, "BPR": 1, "BPRI": 2, "TOP1": 3, "Blackout": 4, "hinge": 5, "logit": 6, "logsig": 7}
@@ -79,6 +79,8 @@ SIGNATURES = {
     "sbr_set_profiling": (C.c_int, [_P, C.c_int]),
     "sbr_stage_times": (C.c_int, [_P, _f32p]),
     "sbr_kernel_launches": (C.c_int64, [_P]),
+    "sbr_timer_start": (C.c_int, [_P]),
+    "sbr_timer_stop": (C.c_int, [_P, _f32p]),
 }
 
 _lib = None
@@ -341,3 +343,11 @@ class Engine(object):
 
     def kernel_launches(self):
         return int(self.lib.sbr_kernel_launches(self._h))
+
+    def timer_start(self):
+        self._check(self.lib.sbr_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._check(self.lib.sbr_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)

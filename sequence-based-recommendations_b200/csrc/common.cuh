@@ -145,6 +145,7 @@ struct sbr_model {
   bool profiling = false;
   bool skip_update = false;
   cudaEvent_t ev[SBR_N_STAGES + 1] = {};
+  cudaEvent_t timer[2] = {};
   float stage_ms[SBR_N_STAGES] = {};
 };
 

@@ -81,7 +81,7 @@ bool load_nccl(std::string* why) {
   return true;
 }
 
-const char* kStageNames[SBR_N_STAGES] = {"h2d", "gather", "rnn_fwd", "output", "rnn_bwd", "scatter", "allreduce", "optimizer"};
+const char* kStageNames[SBR_N_STAGES] = {"h2d", "gather", "rnn_fwd", "output", "rnn_bwd", "wgrad", "scatter", "allreduce", "optimizer"};
 
 __global__ void fill_rows_kernel(float* __restrict__ out, const float* __restrict__ bias, int64_t rows, int cols) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,6 +225,8 @@ extern "C" void sbr_destroy(sbr_model* m) {
   F(m->tgt_off); F(m->tgt_ids); F(m->w_neg); F(m->def_tgt); F(m->excl_off); F(m->excl_ids); F(m->topk_ids);
   if (m->h_len) cudaFreeHost(m->h_len);
   if (m->h_cost) cudaFreeHost(m->h_cost);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
+  for (auto& e : m->timer) if (e) cudaEventDestroy(e);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -302,6 +304,10 @@ static int create_impl(sbr_model* m) {
   }
   CU_TRY(m, cudaMallocHost((void**)&m->h_len, (B + 1) * sizeof(int32_t)));
   CU_TRY(m, cudaMallocHost((void**)&m->h_cost, 4 * sizeof(float)));
+  m->h_stage_bytes = TB * m->K * sizeof(int32_t);
+  CU_TRY(m, cudaMallocHost(&m->h_stage, m->h_stage_bytes));
+  CU_TRY(m, cudaEventCreate(&m->timer[0]));
+  CU_TRY(m, cudaEventCreate(&m->timer[1]));
 
   if (c.n_ranks > 1) {
     std::string why;
@@ -475,7 +481,10 @@ static int stage_common(sbr_model* m, BatchSlot& s, const int32_t* X, const floa
   if (rc) return rc;
   s.B = B;
   s.t_max = t_max;
-  CU_TRY(m, cudaMemcpyAsync(s.X, X, (size_t)B * m->T * m->K * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+  // pageable caller buffer -> pinned staging -> device (one DMA, no driver-side bounce)
+  const size_t xbytes = (size_t)B * m->T * m->K * sizeof(int32_t);
+  memcpy(m->h_stage, X, xbytes);
+  CU_TRY(m, cudaMemcpyAsync(s.X, m->h_stage, xbytes, cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaMemcpyAsync(s.len, m->h_len, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
   // h_len is reused by the next call: the copy must have left the host buffer
   CU_TRY(m, cudaStreamSynchronize(m->stream));
@@ -551,6 +560,7 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
     LayerDesc& L = m->layers[li];
     const int H = L.H, GH = L.G * L.H;
     if ((rc = launch_rnn_backward(m, L, s.len, B, t_max, li == m->L - 1 ? m->dh_last : nullptr))) return rc;
+    if (li == 0) stage_mark(m, 5);
     // dW_hid = sum_t h_{t-1}^T da_t  : one tall-K GEMM outside the scan
     if (L.G == 3) {
       if ((rc = launch_gemm(m, true, false, H, 2 * H, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
@@ -559,7 +569,7 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
       if ((rc = launch_gemm(m, true, false, H, GH, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
     }
     if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
-    if (li == 0) stage_mark(m, 5);
+    if (li == 0) stage_mark(m, 6);
     if (li == 0 && m->E == 0) {
       if ((rc = launch_scatter_add_rows(m, s.X, s.len, L.dXg, m->grads + L.W_in, B, T, K, GH, t_max))) return rc;
     } else {
@@ -598,7 +608,7 @@ static int begin_step(sbr_model* m) {
 
 static int finish_step(sbr_model* m, float* cost) {
   int rc;
-  stage_mark(m, 6);
+  stage_mark(m, 7);
   if (m->nccl_comm) {
     ncclResult_t r = g_nccl.AllReduce(m->grads, m->grads, (size_t)m->P_pad + 1, ncclFloat, ncclSum,
                                       (ncclComm_t)m->nccl_comm, m->stream);
@@ -607,11 +617,11 @@ static int finish_step(sbr_model* m, float* cost) {
       return SBR_E_NCCL;
     }
   }
-  stage_mark(m, 7);
+  stage_mark(m, 8);
   if (cost) CU_TRY(m, cudaMemcpyAsync(m->h_cost, m->grads + m->cost_slot, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   if (!m->skip_update)
     if ((rc = launch_optimizer(m))) return rc;
-  stage_mark(m, 8);
+  stage_mark(m, 9);
   if (cost || m->profiling) {
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     if (cost) *cost = m->h_cost[0];
@@ -848,3 +858,21 @@ extern "C" int sbr_stage_times(sbr_model* m, float ms[SBR_N_STAGES]) {
 }
 
 extern "C" int64_t sbr_kernel_launches(const sbr_model* m) { return m ? m->launches : SBR_E_ARG; }
+
+extern "C" int sbr_timer_start(sbr_model* m) {
+  CHECK_STICKY(m);
+  CU_TRY(m, cudaSetDevice(m->dev));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  CU_TRY(m, cudaEventRecord(m->timer[0], m->stream));
+  return 0;
+}
+
+extern "C" int sbr_timer_stop(sbr_model* m, float* ms) {
+  CHECK_STICKY(m);
+  if (!ms) return SBR_E_ARG;
+  CU_TRY(m, cudaSetDevice(m->dev));
+  CU_TRY(m, cudaEventRecord(m->timer[1], m->stream));
+  CU_TRY(m, cudaEventSynchronize(m->timer[1]));
+  CU_TRY(m, cudaEventElapsedTime(ms, m->timer[0], m->timer[1]));
+  return 0;
+}

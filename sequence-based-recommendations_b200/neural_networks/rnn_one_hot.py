@@ -1,0 +1,38 @@
+"""RNNOneHot -- host mirror of neural_networks/rnn_one_hot.py:13-106: recurrent stack ->
+Dense(n_items, softmax), cost = mean(categorical_crossentropy / popularity**diversity_bias)
+(+ L2/L1 on the output bias).  The arithmetic is `sbr_train_step_cce` (include/sbr_b200.h)."""
+import numpy as np
+
+from . import rnn_base as rnn
+
+
+class RNNOneHot(rnn.RNNBase):
+    loss_name = "CCE"
+
+    def __init__(self, diversity_bias=0.0, regularization=0.0, **kwargs):
+        super().__init__(**kwargs)
+        self.diversity_bias = np.float32(diversity_bias)
+        self.regularization = regularization
+        self.name = "RNN with categorical cross entropy"
+
+    def _get_model_filename(self, epochs):
+        return "rnn_cce_db" + str(self.diversity_bias) + "_r" + str(self.regularization) + "_" + self._common_filename(epochs)
+
+    def _engine_extra_kwargs(self):
+        return dict(regularization=float(self.regularization))
+
+    def _compile_train_function(self):
+        """train_function(X, mask, Y, pop, exclude) -> cost (rnn_one_hot.py:61, rnn_base.py:185).
+        `exclude` is accepted and ignored, as in the reference (on_unused_input='ignore')."""
+        def train_function(X, mask, Y, pop, exclude=None):
+            sl = self._split_rows
+            return self.engine.train_step_cce(sl(X), sl(mask), sl(Y), sl(pop))
+        self.train_function = train_function
+
+    def _prepare_input(self, sequences):
+        """(X, mask, Y, pop, exclude) for a list of [user_id, input_sequence, targets]
+        (rnn_one_hot.py:83-106); `exclude` is the ragged list of seen ids instead of a dense [B,N]."""
+        X, mask, seen = self._fill_inputs(sequences)
+        Y = np.array([int(t[2][0][0]) for t in sequences], dtype=np.int32)       # first and only target
+        pop = np.power(self.dataset.item_popularity[Y], self.diversity_bias).astype(np.float32)
+        return (X, mask, Y, pop, seen)
