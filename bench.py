@@ -176,7 +176,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -320,7 +320,6 @@ def main():
     launches = eng.kernel_launches() - launches0
     last_cost = eng.synchronize(want_cost=True)
     ms = max_over_ranks(ms)
-    clocks = sampler.stop() if rank == 0 else None
     value = B_global * K / (ms * 1e-3)
 
     # ---- leg 2: end to end through the public API, host buffers ------------------------------
@@ -333,6 +332,7 @@ def main():
         cost = pred.train_function(*batches[i])
     eng.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None     # sampled across both timed legs
     barrier()
     e2e_value = B_global * K / e2e_s
     Bl, T = cfg["B"], cfg["T"]

@@ -92,12 +92,21 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int32_t* __
         if (VEC4) {
           for (int c = lane * 4; c < ncols; c += 128) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            unsigned mm = members;
-            while (mm) {
-              const int mlane = __ffs(mm) - 1;
-              mm &= mm - 1;
-              float4 v = ld4(src0 + (int64_t)mlane * ncols + c);
-              s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            if (members == 0xffffffffu) {
+              // common case (nested prefixes): the whole warp shares the id -> 32 independent loads
+#pragma unroll 8
+              for (int mlane = 0; mlane < 32; ++mlane) {
+                const float4 v = ld4(src0 + (int64_t)mlane * ncols + c);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+              }
+            } else {
+              unsigned mm = members;
+              while (mm) {
+                const int mlane = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float4 v = ld4(src0 + (int64_t)mlane * ncols + c);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+              }
             }
             atomicAdd(dst + c, s.x);
             atomicAdd(dst + c + 1, s.y);
