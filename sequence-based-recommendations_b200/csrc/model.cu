@@ -633,7 +633,7 @@ static int finish_step(sbr_model* m, float* cost) {
 
 static int step_cce(sbr_model* m, const BatchSlot& s, float* cost) {
   int rc;
-  const float inv_gb = 1.f / (float)m->global_batch;
+  const float inv_gb = 1.f / (float)(m->cfg.global_batch > 0 ? m->cfg.global_batch : s.B * m->cfg.n_ranks);
   if ((rc = forward_stack(m, s))) return rc;
   const int B = s.B, N = m->N, H = m->H_last;
   if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, N, 1.f, 0.f))) return rc;
@@ -704,7 +704,7 @@ extern "C" int sbr_train_step_sampled(sbr_model* m, const int32_t* X, const floa
   CU_TRY(m, cudaMemcpyAsync(m->cells + n_all, samples, (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaMemcpyAsync(s.pop, pop, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
-  const float inv_gb = 1.f / (float)m->global_batch;
+  const float inv_gb = 1.f / (float)(m->cfg.global_batch > 0 ? m->cfg.global_batch : s.B * m->cfg.n_ranks);
   if ((rc = forward_stack(m, s))) return rc;
   const int H = m->H_last;
   float* bcg = m->bc + nc;   // gradient of the gathered bias entries
@@ -725,7 +725,7 @@ extern "C" int sbr_train_step_sampled(sbr_model* m, const int32_t* X, const floa
 
 static int step_margin(sbr_model* m, const BatchSlot& s, float* cost) {
   int rc;
-  const float inv_gb = 1.f / (float)m->global_batch;
+  const float inv_gb = 1.f / (float)(m->cfg.global_batch > 0 ? m->cfg.global_batch : s.B * m->cfg.n_ranks);
   if ((rc = forward_stack(m, s))) return rc;
   const int B = s.B, N = m->N, H = m->H_last;
   if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, N, 1.f, 0.f))) return rc;
