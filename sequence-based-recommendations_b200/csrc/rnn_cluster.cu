@@ -614,6 +614,10 @@ int dispatch(sbr_model* m, const Plan& p, int n_tiles, const RnnArgs& a) {
 }  // namespace
 
 int launch_rnn_forward(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last) {
+  {
+    const int rc = launch_rnn_forward_tc(m, L, len, B, t_max, h_last);   // tcgen05 3xTF32 scan when it applies
+    if (rc <= 0) return rc;
+  }
   const Plan p = make_plan(m, L.G, L.H, B, false);
   if (p.C == 0) {
     sbr_set_error(m, SBR_E_ARG, "hidden size %d is not supported by the cluster scan (max 512)", L.H);

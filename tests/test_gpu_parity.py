@@ -172,8 +172,11 @@ def test_training_trajectory(updater):
             c_gpu = eng.train_step_cce(X, mask, Y, pop)
             c_ref = O.train_step(spec, vals, upd, X, mask, Y=Y, pop=pop)
             assert abs(float(c_gpu) - float(c_ref)) <= 1e-4, (step, c_gpu, c_ref)
+        # adagrad divides by sqrt(acc + 1e-6): a gradient that is tiny on both sides (|g| << 1e-3) is
+        # amplified by lr / 1e-3 = 50 per step, so its fp32-vs-float64 noise shows up 50x larger
+        ptol = 1e-3 if updater == "adagrad" else 2e-4
         for (name, _), a, b in zip(O.param_names_shapes(spec), vals, eng.get_all_param_values()):
-            assert np.abs(a - b).max() <= 2e-4, name
+            assert np.abs(a - b).max() <= ptol, name
     finally:
         eng.close()
 
