@@ -173,6 +173,7 @@ int launch_rnn_backward(sbr_model* m, const LayerDesc& L, const int32_t* len, in
 
 // rnn_tc.cu (returns 1 when the tcgen05 path does not apply)
 int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last);
+int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last);
 
 // gemm.cu : C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (row-major, beta in {0,1})
 int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,

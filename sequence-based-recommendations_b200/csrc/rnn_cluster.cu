@@ -636,6 +636,10 @@ int launch_rnn_forward(sbr_model* m, const LayerDesc& L, const int32_t* len, int
 
 int launch_rnn_backward(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max,
                         const float* dh_last) {
+  if (!getenv("SBR_DISABLE_TC_BWD")) {
+    const int rc = launch_rnn_backward_tc(m, L, len, B, t_max, dh_last);   // tcgen05 3xTF32 BPTT when it applies
+    if (rc <= 0) return rc;
+  }
   const Plan p = make_plan(m, L.G, L.H, B, true);
   if (p.C == 0) {
     sbr_set_error(m, SBR_E_ARG, "hidden size %d is not supported by the cluster scan (max 512)", L.H);

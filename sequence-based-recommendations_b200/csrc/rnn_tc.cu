@@ -47,7 +47,9 @@ struct TcArgs {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // top 19 bits of v, rounded to nearest: exactly what kind::tf32 reads; lo = v - hi is exact in fp32
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// gate nonlinearities on the SFU: ex2.approx + rcp.approx (relative error ~1e-7 in the working range)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 __device__ __forceinline__ float clipf_(float x, float c) { return c > 0.f ? fminf(fmaxf(x, -c), c) : x; }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -92,6 +94,24 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t cta_addr, uint32_t rank
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// asynchronous 16-byte store into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16)
+// when the data has landed (release at cluster scope) -- no fence, no barrier on the sender side
+__device__ __forceinline__ void st_async_v4(uint32_t addr, float4 v, uint32_t mbar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               :: "r"(addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                  "r"(__float_as_uint(v.w)), "r"(mbar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one elected lane of a converged warp (same idiom as cute::elect_one_sync): lets the compiler keep the
+// tcgen05.mma operands in uniform registers without per-instruction election loops
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\n     elect.sync %%rx|%%px, %2;\n@%%px mov.s32 %1, 1;\n     mov.s32 %0, %%rx;\n}\n"
+               : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFF));
+  return pred;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -122,15 +142,21 @@ __device__ __forceinline__ int bidx(int b, int k) { return (k >> 2) * (TC_BT * 4
 // by the epilogue: the chain into the large accumulator is KS adds instead of 3*KS.
 __device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float* Bhi, const float* Blo,
                                              int KS, uint32_t idesc) {
-  const uint32_t bhi = smem_u32(Bhi), blo = smem_u32(Blo);
-  uint32_t acc = 0;
-  for (int ks = 0; ks < KS; ++ks) {
-    const uint64_t dhi = make_desc(bhi + ks * 2 * (TC_BT * 16), TC_BT * 16, 128);
-    const uint64_t dlo = make_desc(blo + ks * 2 * (TC_BT * 16), TC_BT * 16, 128);
-    mma_ts(tD, tAhi + ks * 8, dhi, idesc, acc);
-    mma_ts(tD + TC_BT, tAhi + ks * 8, dlo, idesc, acc);
-    mma_ts(tD + TC_BT, tAlo + ks * 8, dhi, idesc, 1);
-    acc = 1;
+  // descriptors advance by a constant per k-chunk: 2 core-matrix columns = 2 * 256 B = 32 (16-byte units)
+  uint64_t dhi = make_desc(smem_u32(Bhi), TC_BT * 16, 128);
+  uint64_t dlo = make_desc(smem_u32(Blo), TC_BT * 16, 128);
+  mma_ts(tD, tAhi, dhi, idesc, 0);
+  mma_ts(tD + TC_BT, tAhi, dlo, idesc, 0);
+  mma_ts(tD + TC_BT, tAlo, dhi, idesc, 1);
+#pragma unroll 1
+  for (int ks = 1; ks < KS; ++ks) {
+    dhi += 32;
+    dlo += 32;
+    tAhi += 8;
+    tAlo += 8;
+    mma_ts(tD, tAhi, dhi, idesc, 1);
+    mma_ts(tD + TC_BT, tAhi, dlo, idesc, 1);
+    mma_ts(tD + TC_BT, tAlo, dhi, idesc, 1);
   }
 }
 
@@ -163,8 +189,8 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 
   if (tid < TC_BT) lens_s[tid] = (b0 + tid < B) ? min(a.len[b0 + tid], a.t_max) : 0;
   if (tid == 0) {
-    mbar_init(&raw_full[0], C * (TC_NT / 32));
-    mbar_init(&raw_full[1], C * (TC_NT / 32));
+    mbar_init(&raw_full[0], 1);
+    mbar_init(&raw_full[1], 1);
     mbar_init(&mma_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -262,7 +288,13 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   TC_FENCE_AFTER();
   const int t_end = t_end_s;
   if (t_end > 0) load_x(0, xc);
-  cluster.sync();           // barriers initialised and buffers zeroed everywhere before remote traffic
+  // one phase of raw_full[x] = the complete h_t (16 rows x H units x 4 B) has landed from all owners
+  const uint32_t tx_bytes = (uint32_t)(TC_BT * H * 4);
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&raw_full[0], tx_bytes);
+    mbar_arrive_expect_tx(&raw_full[1], tx_bytes);
+  }
+  cluster.sync();           // barriers initialised and armed everywhere before remote traffic
 
   const uint32_t idesc = make_idesc_tf32(128, TC_BT);
   const uint32_t hraw_addr = smem_u32(hraw);
@@ -276,6 +308,7 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
       // h_{t-1} has landed from every CTA of the cluster; split it into the hi/lo B operand
       const int use = (t - (cur == 0 ? 2 : 1)) >> 1;
       mbar_wait_cluster(&raw_full[cur], use & 1);
+      if (tid == 0) mbar_arrive_expect_tx(&raw_full[cur], tx_bytes);   // arm the next use of this buffer
       const float4* src = reinterpret_cast<const float4*>(hprev);
       float4* dhi = reinterpret_cast<float4*>(Bhi);
       float4* dlo = reinterpret_cast<float4*>(Blo);
@@ -292,9 +325,12 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
       __syncthreads();
       TC_FENCE_AFTER();
     }
-    if (tid == 0) {
-      issue_3xtf32(tD, tAhi, tAlo, Bhi, Blo, KS, idesc);
-      umma_commit(&mma_done);
+    if (warp == 0) {
+      if (elect_one_sync()) {
+        issue_3xtf32(tD, tAhi, tAlo, Bhi, Blo, KS, idesc);
+        umma_commit(&mma_done);
+      }
+      __syncwarp();
     }
     mbar_wait_cta(&mma_done, t & 1);
     TC_FENCE_AFTER();
@@ -328,28 +364,28 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
             const float c_prev = cst[u];
             const float ig = sigmoidf_(xg[0] + pre[0] + c_prev * wci[u]);
             const float fg = sigmoidf_(xg[1] + pre[1] + c_prev * wcf[u]);
-            const float gg = tanhf(xg[2] + pre[2]);
+            const float gg = tanhf_(xg[2] + pre[2]);
             const float c_new = fg * c_prev + ig * gg;
             const float og = sigmoidf_(xg[3] + pre[3] + c_new * wco[u]);
-            hn[u] = og * tanhf(c_new);
+            hn[u] = og * tanhf_(c_new);
             cst[u] = c_new;
             sv[u][0] = ig; sv[u][1] = fg; sv[u][2] = gg; sv[u][3] = og;
           } else if constexpr (G == 3) {
             const float r = sigmoidf_(pre[0] + xg[0]);
             const float uu = sigmoidf_(pre[1] + xg[1]);
             const float ac = pre[2];
-            const float cand = tanhf(xg[2] + r * ac);
+            const float cand = tanhf_(xg[2] + r * ac);
             hn[u] = (1.f - uu) * hp[u] + uu * cand;
             sv[u][0] = r; sv[u][1] = uu; sv[u][2] = cand; sv[u][3] = ac;
           } else {
-            hn[u] = tanhf(xg[0] + pre[0]);
+            hn[u] = tanhf_(xg[0] + pre[0]);
           }
         }
       }
       // publish h_t[b, j0+ju .. +3] (fp32, one 16-byte store) into every CTA of the cluster
       const float4 hv = make_float4(hn[0], hn[1], hn[2], hn[3]);
       const uint32_t off = hraw_addr + (uint32_t)(nxt * Kp * TC_BT + bidx(eb, j0 + ju)) * 4u;
-      for (int rr = 0; rr < C; ++rr) st_cluster_v4(map_to_rank(off, rr), hv);
+      for (int rr = 0; rr < C; ++rr) st_async_v4(map_to_rank(off, rr), hv, map_to_rank(bar_addr[nxt], rr));
       if (row_ok) {
         const int64_t row1 = (int64_t)(t + 1) * B + b0 + eb;
         *reinterpret_cast<float4*>(a.hs + row1 * H + j0 + ju) = hv;
@@ -366,10 +402,6 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     for (int g = 0; g < G; ++g)
 #pragma unroll
       for (int u = 0; u < 4; ++u) xc[g][u] = xn[g][u];
-    // announce: one release-arrive per warp on the next buffer's barrier of every CTA
-    __syncwarp();
-    if (lane == 0)
-      for (int rr = 0; rr < C; ++rr) mbar_arrive_remote(map_to_rank(bar_addr[nxt], rr));
   }
 
   // final state: wait for the last exchange so every CTA can read the full h (only own slice is written)
@@ -388,10 +420,318 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward (BPTT)
+// ------------------------------------------------------------------------------------------------
+// TMEM map (MT = number of 128-row tiles of the hidden index k, Kb = 4*Hs own gate columns):
+//   D1_mt at 32*mt, D2_mt at 32*mt+16; A_mt_hi at 32*MT + mt*2*Kb, A_mt_lo right after it.
+template <int G, int MT>
+__global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = cluster.num_blocks();
+  const int rank = cluster.block_rank();
+  const int tile = blockIdx.x / C;
+  const int b0 = tile * TC_BT;
+  const int H = a.H, Hs = a.Hs, GH = G * H, B = a.B;
+  const int Kb = 4 * Hs;                 // contraction length: own gate columns, kk = 4*j + g
+  const int KS = Kb / 8;
+  const int HP = MT * 128;               // padded hidden extent of the partial dh
+  const int j0 = rank * Hs;
+  const int nj = max(0, min(Hs, H - j0));
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  extern __shared__ __align__(128) float smem[];
+  float* Bhi = smem;                            // [Kb/4][16][4]  da (hi)
+  float* Blo = Bhi + Kb * TC_BT;                // da (lo)
+  float* part = Blo + Kb * TC_BT;               // [2][C][16][Hs] partial dh received from the peers
+  float* dsm = part + 2 * C * TC_BT * Hs;       // [16][HP+4] partial dh of this CTA, row b, column k
+  const int DLD = HP + 4;
+  __shared__ __align__(8) uint64_t part_full[2];
+  __shared__ __align__(8) uint64_t mma_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int lens_s[TC_BT];
+  __shared__ int t_end_s;
+
+  if (tid < TC_BT) lens_s[tid] = (b0 + tid < B) ? min(a.len[b0 + tid], a.t_max) : 0;
+  if (tid == 0) {
+    mbar_init(&part_full[0], 1);
+    mbar_init(&part_full[1], 1);
+    mbar_init(&mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < 2 * Kb * TC_BT; i += TC_NT) Bhi[i] = 0.f;            // Bhi and Blo are contiguous
+  for (int i = tid; i < 2 * C * TC_BT * Hs; i += TC_NT) part[i] = 0.f;
+  TC_FENCE_BEFORE();
+  __syncthreads();
+  TC_FENCE_AFTER();
+  if (tid == 0) {
+    int mx = 0;
+    for (int b = 0; b < TC_BT; ++b) mx = max(mx, lens_s[b]);
+    t_end_s = mx;
+  }
+  const uint32_t tmem = tmem_base_s;
+
+  // ---- A operand tiles: row = hidden index k, column kk = 4*j + g  <->  W_hid[k][g*H + j0 + j]
+  {
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int mt = 0; mt < MT; ++mt) {
+      const int k = mt * 128 + tid;
+      const float* src = a.W_hid + (int64_t)k * GH + j0;
+      const uint32_t tAhi = tmem + 32 * MT + mt * 2 * Kb, tAlo = tAhi + Kb;
+      for (int c0 = 0; c0 < Kb; c0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kk = c0 + i, j = kk >> 2, g = kk & 3;
+          const float v = (k < H && g < G && j < nj) ? __ldg(src + g * H + j) : 0.f;
+          const float h = tf32_hi(v);
+          hi[i] = __float_as_uint(h);
+          lo[i] = __float_as_uint(v - h);
+        }
+        tmem_st8(tAhi + lane_off + c0, hi);
+        tmem_st8(tAlo + lane_off + c0, lo);
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+
+  const int eb = tid >> 3, jq = tid & 7;
+  const int ju = 4 * jq;
+  const bool own = ju < nj;
+  const bool row_ok = b0 + eb < B;
+  float carry[4], dcs[4], dpe[4][3], wci[4], wcf[4], wco[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    carry[u] = (a.dh_last && own && row_ok) ? a.dh_last[(int64_t)(b0 + eb) * H + j0 + ju + u] : 0.f;
+    dcs[u] = 0.f;
+    dpe[u][0] = dpe[u][1] = dpe[u][2] = 0.f;
+    wci[u] = wcf[u] = wco[u] = 0.f;
+    if (G == 4 && own) {
+      wci[u] = a.peep[j0 + ju + u];
+      wcf[u] = a.peep[H + j0 + ju + u];
+      wco[u] = a.peep[2 * H + j0 + ju + u];
+    }
+  }
+  TC_FENCE_BEFORE();
+  __syncthreads();
+  TC_FENCE_AFTER();
+  const int t_end = t_end_s;
+
+  // masked tail [t_end, t_max): exactly zero gradients
+  for (int t = t_end; t < a.t_max; ++t) {
+    if (own && row_ok) {
+      const int64_t row = (int64_t)t * B + b0 + eb;
+#pragma unroll
+      for (int g = 0; g < G; ++g) *reinterpret_cast<float4*>(a.dXg + row * GH + g * H + j0 + ju) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (G == 3) *reinterpret_cast<float4*>(a.dac + row * H + j0 + ju) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
+  // saved tensors of a step for this thread's 4 units: [slot][unit]
+  //  LSTM: i f g o c_prev c_new | GRU: r u cand a_c h_prev | Vanilla: h_new ; last slot: dhs from above
+  constexpr int NSAVE = (G == 4) ? 6 : (G == 3 ? 5 : 1);
+  float sv[NSAVE + 1][4], svn[NSAVE + 1][4];
+#pragma unroll
+  for (int s = 0; s <= NSAVE; ++s)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sv[s][u] = svn[s][u] = 0.f;
+  auto ld4f = [](const float* p, float (&d)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  };
+  auto load_saved = [&](int t, float (&s)[NSAVE + 1][4]) {
+    if (own && t < lens_s[eb]) {
+      const int64_t row = (int64_t)t * B + b0 + eb;
+      if constexpr (G == 4) {
+        const float* ap = a.act + row * 4 * H + j0 + ju;
+        ld4f(ap, s[0]); ld4f(ap + H, s[1]); ld4f(ap + 2 * H, s[2]); ld4f(ap + 3 * H, s[3]);
+        ld4f(a.cs + row * H + j0 + ju, s[4]);
+        ld4f(a.cs + (row + B) * H + j0 + ju, s[5]);
+      } else if constexpr (G == 3) {
+        const float* ap = a.act + row * 4 * H + j0 + ju;
+        ld4f(ap, s[0]); ld4f(ap + H, s[1]); ld4f(ap + 2 * H, s[2]); ld4f(ap + 3 * H, s[3]);
+        ld4f(a.hs + row * H + j0 + ju, s[4]);
+      } else {
+        ld4f(a.hs + (row + B) * H + j0 + ju, s[0]);
+      }
+      if (a.dhs) ld4f(a.dhs + row * H + j0 + ju, s[NSAVE]);
+    }
+  };
+  if (t_end > 0) load_saved(t_end - 1, sv);
+
+  // one phase of part_full[x] = the partial dh of my Hs units has landed from all C CTAs
+  const uint32_t tx_bytes = (uint32_t)(C * TC_BT * nj * 4);
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&part_full[0], tx_bytes);
+    mbar_arrive_expect_tx(&part_full[1], tx_bytes);
+  }
+  cluster.sync();
+
+  const uint32_t idesc = make_idesc_tf32(128, TC_BT);
+  const uint32_t part_addr = smem_u32(part);
+  const uint32_t bar_addr[2] = {smem_u32(&part_full[0]), smem_u32(&part_full[1])};
+  int n_wait[2] = {0, 0};      // completed phases of each part_full barrier
+
+  for (int t = t_end - 1; t >= 0; --t) {
+    const int par = t & 1, rpar = par ^ 1;
+    if (t > 0) load_saved(t - 1, svn);
+
+    // ---- phase A: dh_t = carry + partials of step t+1 (+ gradient from the layer above); gate gradients
+    if (t < t_end - 1) {
+      mbar_wait_cluster(&part_full[rpar], n_wait[rpar] & 1);
+      n_wait[rpar]++;
+      if (tid == 0) mbar_arrive_expect_tx(&part_full[rpar], tx_bytes);
+    }
+    if (own) {
+      float dh[4] = {carry[0], carry[1], carry[2], carry[3]};
+      if (t < t_end - 1) {
+        for (int src = 0; src < C; ++src) {
+          const float4 p = *reinterpret_cast<const float4*>(part + ((rpar * C + src) * TC_BT + eb) * Hs + ju);
+          dh[0] += p.x; dh[1] += p.y; dh[2] += p.z; dh[3] += p.w;
+        }
+      }
+      const bool active = t < lens_s[eb];
+      const int64_t row = (int64_t)t * B + b0 + eb;
+      float da[4][4], dx[4][4];   // [unit][gate]
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) da[u][g] = dx[u][g] = 0.f;
+        float carry_new = dh[u];
+        if (active) {
+          const float d = dh[u] + sv[NSAVE][u];
+          if constexpr (G == 4) {
+            const float ig = sv[0][u], fg = sv[1][u], gg = sv[2][u], og = sv[3][u];
+            const float c_prev = sv[4][u], c_new = sv[5][u];
+            const float tc = tanhf_(c_new);
+            const float do_pre = d * tc * og * (1.f - og);
+            const float dct = dcs[u] + d * og * (1.f - tc * tc) + do_pre * wco[u];
+            const float di_pre = dct * gg * ig * (1.f - ig);
+            const float df_pre = dct * c_prev * fg * (1.f - fg);
+            const float dg_pre = dct * ig * (1.f - gg * gg);
+            dpe[u][0] += di_pre * c_prev;
+            dpe[u][1] += df_pre * c_prev;
+            dpe[u][2] += do_pre * c_new;
+            dcs[u] = dct * fg + di_pre * wci[u] + df_pre * wcf[u];
+            da[u][0] = clipf_(di_pre, a.clip);
+            da[u][1] = clipf_(df_pre, a.clip);
+            da[u][2] = clipf_(dg_pre, a.clip);
+            da[u][3] = clipf_(do_pre, a.clip);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dx[u][g] = da[u][g];
+            carry_new = 0.f;
+          } else if constexpr (G == 3) {
+            const float r = sv[0][u], uu = sv[1][u], cand = sv[2][u], ac = sv[3][u], h_prev = sv[4][u];
+            const float du_pre = d * (cand - h_prev) * uu * (1.f - uu);
+            const float dq = clipf_(d * uu * (1.f - cand * cand), a.clip);
+            const float dr_pre = dq * ac * r * (1.f - r);
+            da[u][0] = clipf_(dr_pre, a.clip);
+            da[u][1] = clipf_(du_pre, a.clip);
+            da[u][2] = clipf_(dq * r, a.clip);
+            dx[u][0] = da[u][0];
+            dx[u][1] = da[u][1];
+            dx[u][2] = dq;
+            carry_new = d * (1.f - uu);
+          } else {
+            const float h_new = sv[0][u];
+            const float dq = clipf_(d * (1.f - h_new * h_new), a.clip);
+            da[u][0] = dq;
+            dx[u][0] = dq;
+            carry_new = 0.f;
+          }
+        }
+        carry[u] = carry_new;
+        // B operand element (row eb, kk = 4*(ju+u) + g): one 16-byte store per unit, hi and lo
+        float4 h4, l4;
+        h4.x = tf32_hi(da[u][0]); h4.y = tf32_hi(da[u][1]); h4.z = tf32_hi(da[u][2]); h4.w = tf32_hi(da[u][3]);
+        l4.x = da[u][0] - h4.x; l4.y = da[u][1] - h4.y; l4.z = da[u][2] - h4.z; l4.w = da[u][3] - h4.w;
+        *reinterpret_cast<float4*>(Bhi + (ju + u) * (TC_BT * 4) + eb * 4) = h4;
+        *reinterpret_cast<float4*>(Blo + (ju + u) * (TC_BT * 4) + eb * 4) = l4;
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          *reinterpret_cast<float4*>(a.dXg + row * GH + g * H + j0 + ju) = make_float4(dx[0][g], dx[1][g], dx[2][g], dx[3][g]);
+        if (G == 3) *reinterpret_cast<float4*>(a.dac + row * H + j0 + ju) = make_float4(da[0][2], da[1][2], da[2][2], da[3][2]);
+      }
+    }
+    PROXY_FENCE_SMEM();
+    TC_FENCE_BEFORE();
+    __syncthreads();
+    TC_FENCE_AFTER();
+
+    // ---- phase B: partial dh_{t-1}[b][k] = sum_kk da[b][kk] * W_hid[k][kk], all k (MT tiles of 128 rows)
+    if (warp == 0) {
+      if (elect_one_sync()) {
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t tAhi = tmem + 32 * MT + mt * 2 * Kb;
+          issue_3xtf32(tmem + 32 * mt, tAhi, tAhi + Kb, Bhi, Blo, KS, idesc);
+        }
+        umma_commit(&mma_done);
+      }
+      __syncwarp();
+    }
+    mbar_wait_cta(&mma_done, (t_end - 1 - t) & 1);
+    TC_FENCE_AFTER();
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float v[16], w[16];
+      tmem_ld16(tmem + 32 * mt + ((uint32_t)(warp * 32) << 16), v);
+      tmem_ld16(tmem + 32 * mt + 16 + ((uint32_t)(warp * 32) << 16), w);
+#pragma unroll
+      for (int b = 0; b < 16; ++b) dsm[b * DLD + mt * 128 + tid] = v[b] + w[b];
+    }
+    TC_FENCE_BEFORE();
+    __syncthreads();
+
+    // ---- phase C: reduce-scatter: quad (row b, k = 4q..4q+3) goes to the owner of k, slot [par][my rank]
+    for (int i = tid; i < TC_BT * (H / 4); i += TC_NT) {
+      const int b = i / (H / 4), q = i - b * (H / 4);
+      const int k = 4 * q;
+      const int rr = k / Hs, jo = k - rr * Hs;
+      const float4 v = *reinterpret_cast<const float4*>(dsm + b * DLD + k);
+      const uint32_t off = part_addr + (uint32_t)(((par * C + rank) * TC_BT + b) * Hs + jo) * 4u;
+      st_async_v4(map_to_rank(off, rr), v, map_to_rank(bar_addr[par], rr));
+    }
+#pragma unroll
+    for (int s = 0; s <= NSAVE; ++s)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sv[s][u] = svn[s][u];
+  }
+
+  // ---- gradients of the learned initial states and of the peepholes
+  if (t_end > 0) {
+    mbar_wait_cluster(&part_full[0], n_wait[0] & 1);   // step t = 0 wrote buffer 0
+  }
+  if (own && row_ok) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float dh = carry[u];
+      if (t_end > 0)
+        for (int src = 0; src < C; ++src) dh += part[((0 * C + src) * TC_BT + eb) * Hs + ju + u];
+      atomicAdd(a.g_h_init + j0 + ju + u, dh);
+      if (G == 4) {
+        atomicAdd(a.g_c_init + j0 + ju + u, dcs[u]);
+        atomicAdd(a.g_peep + j0 + ju + u, dpe[u][0]);
+        atomicAdd(a.g_peep + H + j0 + ju + u, dpe[u][1]);
+        atomicAdd(a.g_peep + 2 * H + j0 + ju + u, dpe[u][2]);
+      }
+    }
+  }
+  TC_FENCE_BEFORE();
+  cluster.sync();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch plumbing
 // ------------------------------------------------------------------------------------------------
-struct TcPlan { int C, Hs, Kp; size_t smem; bool ok; };
+struct TcPlan { int C, Hs, Kp, MT; size_t smem, smem_bwd; bool ok, bwd_ok; };
 
 TcPlan tc_plan(int G, int H) {
   TcPlan p{};
@@ -408,6 +748,11 @@ TcPlan tc_plan(int G, int H) {
   if (!p.ok) return p;
   size_t f = (size_t)4 * p.Kp * TC_BT + (size_t)TC_BT * GSM_LD;
   p.smem = std::max<size_t>(f * sizeof(float), 120 * 1024);   // > half an SM: one CTA (one TMEM allocation) per SM
+  // backward: MT tiles of 128 hidden rows, Kb = 4*Hs own gate columns, hi+lo: 32*MT + 2*MT*Kb TMEM columns
+  p.MT = cdiv(H, 128);
+  p.bwd_ok = (32 * p.MT + 2 * p.MT * 4 * p.Hs) <= 512;
+  size_t fb = (size_t)2 * 4 * p.Hs * TC_BT + (size_t)2 * p.C * TC_BT * p.Hs + (size_t)TC_BT * (p.MT * 128 + 4);
+  p.smem_bwd = std::max<size_t>(fb * sizeof(float), 120 * 1024);
   return p;
 }
 
@@ -448,4 +793,20 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   if (L.G == 4) return launch_tc(m, rnn_fwd_tc_kernel<4>, p, n_tiles, a);
   if (L.G == 3) return launch_tc(m, rnn_fwd_tc_kernel<3>, p, n_tiles, a);
   return launch_tc(m, rnn_fwd_tc_kernel<1>, p, n_tiles, a);
+}
+
+int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last) {
+  TcPlan p = tc_plan(L.G, L.H);
+  if (!p.ok || !p.bwd_ok) return 1;
+  p.smem = p.smem_bwd;
+  TcArgs a{};
+  a.W_hid = m->params + L.W_hid; a.peep = m->params + L.peep; a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act;
+  a.dh_last = dh_last; a.dhs = dh_last ? nullptr : L.dhs; a.dXg = L.dXg; a.dac = L.dac;
+  a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
+  a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
+  const int n_tiles = cdiv(B, TC_BT);
+#define SBR_BWD_CASE(G_, MT_) if (L.G == G_ && p.MT == MT_) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_>, p, n_tiles, a);
+  SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)
+#undef SBR_BWD_CASE
+  return 1;
 }

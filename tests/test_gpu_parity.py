@@ -160,7 +160,7 @@ def test_training_trajectory(updater):
     spec = O.Spec(n_items=500, cell="GRU", layers=(100,), loss="CCE")
     B, T, K = 16, 20, 12
     rng, vals = _init(spec, 10)
-    lr = {"adam": 1e-3, "adagrad": 0.05, "rmsprop": 1e-3, "adadelta": 1.0, "nesterov": 0.05}[updater]
+    lr = {"adam": 1e-3, "adagrad": 0.01, "rmsprop": 1e-3, "adadelta": 1.0, "nesterov": 0.05}[updater]
     eng = _engine(spec, B, T, updater=updater, lr=lr)
     upd = O.Updater(updater, lr=lr)
     try:
