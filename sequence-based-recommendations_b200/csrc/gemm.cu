@@ -111,6 +111,94 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
   }
 }
 
+
+// ---- specialised C += A^T B for K-slow operands (A stored [K, lda], B stored [K, ldb]): the BPTT weight
+// gradients dW = sum_rows in[row,:]^T dXg[row,:].  Both tiles are copied global->shared with 16-byte
+// cp.async exactly in the layout the FMA loop reads (no transposition), 3-stage pipeline.
+constexpr int TN_BK = 16, TN_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256) sgemm_tn_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                        int ldc, float alpha, int k_per_split, int accumulate) {
+  extern __shared__ __align__(16) float tn_smem[];
+  float (*As)[TN_BK][BM] = reinterpret_cast<float (*)[TN_BK][BM]>(tn_smem);
+  float (*Bs)[TN_BK][BN] = reinterpret_cast<float (*)[TN_BK][BN]>(tn_smem + TN_STAGES * TN_BK * BM);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const int n_tiles = (k_end - k_begin + TN_BK - 1) / TN_BK;
+
+  auto issue = [&](int tile, int stage) {
+    const int k0 = k_begin + tile * TN_BK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256;          // 512 float4 per operand tile
+      const int kk = idx >> 5, c4 = (idx & 31) * 4;
+      const int gk = k0 + kk;
+      const bool kin = gk < k_end;
+      const bool ain = kin && (m0 + c4 < M);
+      const bool bin = kin && (n0 + c4 < N);
+      cp_async16(&As[stage][kk][c4], ain ? A + (int64_t)gk * lda + m0 + c4 : A, ain ? 16 : 0);
+      cp_async16(&Bs[stage][kk][c4], bin ? B + (int64_t)gk * ldb + n0 + c4 : B, bin ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int s = 0; s < TN_STAGES - 1; ++s) {
+    if (s < n_tiles) issue(s, s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    asm volatile("cp.async.wait_group %0;" :: "n"(TN_STAGES - 2) : "memory");
+    __syncthreads();
+    const int nxt = tile + TN_STAGES - 1;
+    if (nxt < n_tiles) issue(nxt, nxt % TN_STAGES);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const int st = tile % TN_STAGES;
+#pragma unroll
+    for (int kk = 0; kk < TN_BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[st][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[st][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[st][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[st][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  const bool atomic_out = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= N) continue;
+      float* c = C + (int64_t)gm * ldc + gn;
+      const float v = alpha * acc[i][j];
+      if (atomic_out) atomicAdd(c, v);
+      else if (accumulate) *c += v;
+      else *c = v;
+    }
+  }
+}
+
 __global__ void zero_matrix_kernel(float* C, int M, int N, int ldc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
@@ -129,10 +217,10 @@ int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   int splits = 1;
   if (K > 0) {
-    splits = std::max(1, std::min(cdiv(2 * m->n_sm, tiles), cdiv(K, 64)));
+    splits = std::max(1, std::min((2 * m->n_sm) / tiles, cdiv(K, 64)));   // <= 2 CTAs per SM: a single wave
     if (tiles >= m->n_sm) splits = 1;
   }
-  int kps = K > 0 ? (int)round_up(cdiv(K, splits), BK) : BK;
+  int kps = K > 0 ? (int)round_up(cdiv(K, splits), 16) : 16;
   splits = K > 0 ? cdiv(K, kps) : 1;
   if (splits > 1 && beta == 0.f) {
     if (ldc == N) {
@@ -145,6 +233,18 @@ int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float
   }
   const dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
   const int accumulate = beta == 1.f ? 1 : 0;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+  if (ta && !tb && al16 && M % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && K >= 64) {
+    const size_t smem = (size_t)TN_STAGES * TN_BK * (BM + BN) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(sgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    sgemm_tn_kernel<<<grid, 256, smem, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
+    KERNEL_CHECK(m);
+    return 0;
+  }
   if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
   else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
   else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
