@@ -85,6 +85,9 @@ struct sbr_model {
   int dev = 0;
   int n_sm = SBR_NSM;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;        // off-critical-path work (see side_fork / side_join in model.cu)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_pending = false;
   std::string err;
   int err_code = 0;
   int64_t launches = 0;

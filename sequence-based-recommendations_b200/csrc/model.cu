@@ -228,6 +228,9 @@ extern "C" void sbr_destroy(sbr_model* m) {
   if (m->h_stage) cudaFreeHost(m->h_stage);
   for (auto& e : m->timer) if (e) cudaEventDestroy(e);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -243,6 +246,9 @@ static int create_impl(sbr_model* m) {
   }
   m->n_sm = prop.multiProcessorCount;
   CU_TRY(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CU_TRY(m, cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+  CU_TRY(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  CU_TRY(m, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   for (auto& e : m->ev) CU_TRY(m, cudaEventCreate(&e));
   build_layout(m);
 
@@ -551,6 +557,9 @@ static int forward_stack(sbr_model* m, const BatchSlot& s) {
   return 0;
 }
 
+static int side_fork(sbr_model* m);
+static int side_return(sbr_model* m);
+
 // BPTT through the stack given m->dh_last; fills the gradient arena of every stack parameter
 static int backward_stack(sbr_model* m, const BatchSlot& s) {
   const int B = s.B, T = m->T, K = m->K, t_max = s.t_max;
@@ -561,6 +570,15 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
     const int H = L.H, GH = L.G * L.H;
     if ((rc = launch_rnn_backward(m, L, s.len, B, t_max, li == m->L - 1 ? m->dh_last : nullptr))) return rc;
     if (li == 0) stage_mark(m, 5);
+    const bool gather_layer = (li == 0 && m->E == 0);
+    if (gather_layer) {
+      // dW_in scatter on the side stream, concurrent with the weight-gradient GEMM below
+      if ((rc = side_fork(m))) return rc;
+      rc = launch_scatter_add_rows(m, s.X, s.len, L.dXg, m->grads + L.W_in, B, T, K, GH, t_max);
+      side_return(m);
+      m->side_pending = true;
+      if (rc) return rc;
+    }
     // dW_hid = sum_t h_{t-1}^T da_t  : one tall-K GEMM outside the scan
     if (L.G == 3) {
       if ((rc = launch_gemm(m, true, false, H, 2 * H, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
@@ -570,9 +588,7 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
     }
     if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
     if (li == 0) stage_mark(m, 6);
-    if (li == 0 && m->E == 0) {
-      if ((rc = launch_scatter_add_rows(m, s.X, s.len, L.dXg, m->grads + L.W_in, B, T, K, GH, t_max))) return rc;
-    } else {
+    if (!gather_layer) {
       const float* in;
       float* din;
       int I;
@@ -587,14 +603,38 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
   return 0;
 }
 
+// Fork / join of the side stream: work that is off the critical path (the output-layer weight gradients
+// while the BPTT scan runs on 64 of the 148 SMs; the scatter while the weight-gradient GEMM runs) is
+// launched on m->side between side_fork() and side_join(); the two streams write disjoint gradient blocks.
+static int side_fork(sbr_model* m) {
+  CU_TRY(m, cudaEventRecord(m->ev_fork, m->stream));
+  CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+  std::swap(m->stream, m->side);     // launchers use m->stream
+  return 0;
+}
+static int side_return(sbr_model* m) {   // back to the main stream; the side work keeps running
+  std::swap(m->stream, m->side);
+  return 0;
+}
+static int side_join(sbr_model* m) {
+  CU_TRY(m, cudaEventRecord(m->ev_join, m->side));
+  CU_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+  return 0;
+}
+
 // gradient of a full-catalog score matrix d[B,N] (already in m->logits): dW_out^T, db, dh_last
 static int output_backward_full(sbr_model* m, int B) {
   const int N = m->N, H = m->H_last;
   int rc;
-  if ((rc = launch_gemm(m, true, false, N, H, B, m->logits, N, m->h_last, H, m->grads + m->out_WT, H, 1.f, 1.f))) return rc;
-  if ((rc = launch_colsum(m, m->logits, B, N, N, m->grads + m->out_b))) return rc;
+  // critical path: dh_last feeds the BPTT scan
   if ((rc = launch_gemm(m, false, false, B, H, N, m->logits, N, m->params + m->out_WT, H, m->dh_last, H, 1.f, 0.f))) return rc;
-  return 0;
+  // off the critical path: dW_out^T and db_out on the side stream, joined before the all-reduce
+  if ((rc = side_fork(m))) return rc;
+  rc = launch_gemm(m, true, false, N, H, B, m->logits, N, m->h_last, H, m->grads + m->out_WT, H, 1.f, 1.f);
+  if (!rc) rc = launch_colsum(m, m->logits, B, N, N, m->grads + m->out_b);
+  side_return(m);
+  m->side_pending = true;
+  return rc;
 }
 
 static int begin_step(sbr_model* m) {
@@ -608,6 +648,10 @@ static int begin_step(sbr_model* m) {
 
 static int finish_step(sbr_model* m, float* cost) {
   int rc;
+  if (m->side_pending) {
+    if ((rc = side_join(m))) return rc;
+    m->side_pending = false;
+  }
   stage_mark(m, 7);
   if (m->nccl_comm) {
     ncclResult_t r = g_nccl.AllReduce(m->grads, m->grads, (size_t)m->P_pad + 1, ncclFloat, ncclSum,

@@ -42,6 +42,7 @@ struct TcArgs {
   const float* dh_last; const float* dhs; float* dXg; float* dac; float* g_peep; float* g_h_init; float* g_c_init;
   float clip;
   int B, H, Hs, Kp, t_max;
+  long long* dbg;   // optional phase timeline of CTA 0 / thread 0 (8 stamps per step)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,6 +102,13 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, float4 v, uint32_t mb
                :: "r"(addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
                   "r"(__float_as_uint(v.w)), "r"(mbar_addr) : "memory");
 }
+// bulk asynchronous copy of a contiguous block of THIS CTA's shared memory into a peer CTA's shared memory
+// (TMA engine, no per-thread stores); the peer's mbarrier receives complete_tx(bytes) when it has landed
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -140,18 +148,34 @@ __device__ __forceinline__ int bidx(int b, int k) { return (k >> 2) * (TC_BT * 4
 // accumulator add of the tensor core truncates, so the large term and the 2^-11-times-smaller
 // correction terms are kept in separate TMEM accumulators (D2 = D1 + 16 columns) and summed in fp32
 // by the epilogue: the chain into the large accumulator is KS adds instead of 3*KS.
-__device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float* Bhi, const float* Blo,
-                                             int KS, uint32_t idesc) {
-  // descriptors advance by a constant per k-chunk: 2 core-matrix columns = 2 * 256 B = 32 (16-byte units)
-  uint64_t dhi = make_desc(smem_u32(Bhi), TC_BT * 16, 128);
-  uint64_t dlo = make_desc(smem_u32(Blo), TC_BT * 16, 128);
+// one accumulation chain: D[128x16] (=|+=) sum_ks A(ks) * B(ks); each chain is issued by its own warp so that
+// the (issue-bound) tensor-core work of a step is spread over several instruction streams
+__device__ __forceinline__ void issue_chain(uint32_t tD, uint32_t tA, uint32_t b_addr, uint32_t lbo_bytes, int KS,
+                                            uint32_t idesc, uint32_t acc_first) {
+  uint64_t d = make_desc(b_addr, lbo_bytes, 128);
+  const uint64_t adv = (uint64_t)(2 * lbo_bytes) >> 4;
+  mma_ts(tD, tA, d, idesc, acc_first);
+#pragma unroll 4
+  for (int ks = 1; ks < KS; ++ks) {
+    d += adv;
+    tA += 8;
+    mma_ts(tD, tA, d, idesc, 1);
+  }
+}
+
+__device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tAhi, uint32_t tAlo, uint32_t bhi_addr, uint32_t blo_addr,
+                                             uint32_t lbo_bytes, int KS, uint32_t idesc) {
+  // descriptors advance by a constant per k-chunk: 2 core-matrix columns = 2 * LBO bytes
+  uint64_t dhi = make_desc(bhi_addr, lbo_bytes, 128);
+  uint64_t dlo = make_desc(blo_addr, lbo_bytes, 128);
+  const uint64_t adv = (uint64_t)(2 * lbo_bytes) >> 4;
   mma_ts(tD, tAhi, dhi, idesc, 0);
   mma_ts(tD + TC_BT, tAhi, dlo, idesc, 0);
   mma_ts(tD + TC_BT, tAlo, dhi, idesc, 1);
 #pragma unroll 1
   for (int ks = 1; ks < KS; ++ks) {
-    dhi += 32;
-    dlo += 32;
+    dhi += adv;
+    dlo += adv;
     tAhi += 8;
     tAlo += 8;
     mma_ts(tD, tAhi, dhi, idesc, 1);
@@ -163,8 +187,11 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tAhi, uint32_
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+constexpr int FWD_NT = 256;  // forward: 8 warps (warp w reaches TMEM lane quadrant w % 4)
+constexpr int NU = 2;        // hidden units per thread in the forward gate math
+
 template <int G>
-__global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
@@ -174,24 +201,29 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   const int KS = Kp / 8;
   const int j0 = rank * Hs;
   const int nj = max(0, min(Hs, H - j0));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int quad = warp & 3;
+  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
   extern __shared__ __align__(128) float smem[];
-  float* hraw = smem;                            // [2][Kp/4][16][4] fp32 h_{t-1}, written by every CTA of the cluster
-  float* Bhi = hraw + 2 * Kp * TC_BT;            // [Kp/4][16][4]
-  float* Blo = Bhi + Kp * TC_BT;
-  float* gsm = Blo + Kp * TC_BT;                 // [16][GSM_LD] gate pre-activations, row b, column m = 4j+g
+  // h exchange buffers = the MMA B operand itself: hbuf[2][Kp/4][hi|lo][16][4]; every CTA keeps the FULL h_{t-1}
+  // (hi and lo = h - hi), its own Hs-unit slice written locally, the rest bulk-copied in by the owners
+  float* hbuf = smem;
+  const int HB = Kp * TC_BT * 2;                 // floats per buffer (Kp/4 blocks of 128 floats)
+  float* gsm = hbuf + 2 * HB;                    // [16][GSM_LD] gate pre-activations, row b, column m = 4j+g
   __shared__ __align__(8) uint64_t raw_full[2];
   __shared__ __align__(8) uint64_t mma_done;
   __shared__ uint32_t tmem_base_s;
   __shared__ int lens_s[TC_BT];
   __shared__ int t_end_s;
 
+#define TC_KSTAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) a.dbg[512 + (i)] = clock64(); } while (0)
+  TC_KSTAMP(0);
   if (tid < TC_BT) lens_s[tid] = (b0 + tid < B) ? min(a.len[b0 + tid], a.t_max) : 0;
   if (tid == 0) {
     mbar_init(&raw_full[0], 1);
     mbar_init(&raw_full[1], 1);
-    mbar_init(&mma_done, 1);
+    mbar_init(&mma_done, 3);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -199,15 +231,15 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // h_{-1} = learned init, broadcast over the rows: straight into the split B operand
-  for (int i = tid; i < Kp * TC_BT; i += TC_NT) {
+  for (int i = tid; i < Kp * TC_BT; i += FWD_NT) {
     const int kc = i / (TC_BT * 4), rem = i - kc * (TC_BT * 4);
     const int k = kc * 4 + (rem & 3);
     const float v = k < H ? a.h_init[k] : 0.f;
     const float hi = tf32_hi(v);
-    Bhi[i] = hi;
-    Blo[i] = v - hi;
-    hraw[i] = v;               // buffer 0 doubles as "h_prev" of step 0
-    hraw[Kp * TC_BT + i] = 0.f;
+    hbuf[kc * 128 + rem] = hi;
+    hbuf[kc * 128 + 64 + rem] = v - hi;
+    hbuf[HB + kc * 128 + rem] = 0.f;
+    hbuf[HB + kc * 128 + 64 + rem] = 0.f;
   }
   TC_FENCE_BEFORE();
   __syncthreads();
@@ -218,41 +250,42 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     t_end_s = mx;
   }
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tD = tmem;                 // 16 columns
-  const uint32_t tAhi = tmem + 32;          // Kp columns
-  const uint32_t tAlo = tmem + 32 + Kp;     // Kp columns (32 + 2*Kp <= 512)
+  const uint32_t tD = tmem;                 // three 16-column accumulators: hi*hi, hi*lo, lo*hi
+  const uint32_t tAhi = tmem + 64;          // Kp columns
+  const uint32_t tAlo = tmem + 64 + Kp;     // Kp columns (64 + 2*Kp <= 512)
 
-  // ---- A operand: row m = tid = 4*j + g  <->  W_hid[:, g*H + j0 + j]; K along the TMEM columns
+  // ---- A operand: row m = 4*j + g  <->  W_hid[:, g*H + j0 + j]; K along the TMEM columns.
+  //      warps 0-3 stage the hi copy, warps 4-7 the lo copy (same lane quadrants)
   {
-    const int j = tid >> 2, g = tid & 3;
+    const int m = quad * 32 + (tid & 31);
+    const int j = m >> 2, g = m & 3;
     const bool live = (g < G) && (j < nj);
+    const bool want_lo = warp >= 4;
     const float* src = a.W_hidT + (int64_t)(g * H + j0 + j) * H;   // k contiguous
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t dst = (want_lo ? tAlo : tAhi) + lane_off;
     for (int k0 = 0; k0 < Kp; k0 += 8) {
-      uint32_t hi[8], lo[8];
+      uint32_t r[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float v = (live && k0 + i < H) ? __ldg(src + k0 + i) : 0.f;
         const float h = tf32_hi(v);
-        hi[i] = __float_as_uint(h);
-        lo[i] = __float_as_uint(v - h);
+        r[i] = __float_as_uint(want_lo ? v - h : h);
       }
-      tmem_st8(tAhi + lane_off + k0, hi);
-      tmem_st8(tAlo + lane_off + k0, lo);
+      tmem_st8(dst + k0, r);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 
-  // ---- per-thread ownership for the gate math: row b = tid/8, units 4*jq .. 4*jq+3 of the slice
-  const int eb = tid >> 3, jq = tid & 7;
-  const int ju = 4 * jq;
-  const bool own = ju < nj;                       // nj is a multiple of 4 (H % 4 == 0, Hs % 4 == 0)
+  TC_KSTAMP(1);
+  // ---- gate-math ownership: row eb, units ju, ju+1 of the slice (two threads share one 16-byte quad)
+  const int eb = tid >> 4, jq = (tid >> 1) & 7, half = tid & 1;
+  const int ju = 4 * jq + NU * half;
+  const bool own = 4 * jq < nj;                   // nj is a multiple of 4 (H % 4 == 0, Hs % 4 == 0)
   const bool row_ok = b0 + eb < B;
-  float cst[4] = {0.f, 0.f, 0.f, 0.f};
-  float wci[4], wcf[4], wco[4];
+  float cst[NU], wci[NU], wcf[NU], wco[NU];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    wci[u] = wcf[u] = wco[u] = 0.f;
+  for (int u = 0; u < NU; ++u) {
+    cst[u] = wci[u] = wcf[u] = wco[u] = 0.f;
     if (G == 4 && own) {
       wci[u] = a.peep[j0 + ju + u];
       wcf[u] = a.peep[H + j0 + ju + u];
@@ -262,34 +295,34 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   }
   if (own && row_ok) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) {
       a.hs[(int64_t)(b0 + eb) * H + j0 + ju + u] = a.h_init[j0 + ju + u];
       if (G == 4) a.cs[(int64_t)(b0 + eb) * H + j0 + ju + u] = a.c_init[j0 + ju + u];
     }
   }
-  float xc[G][4], xn[G][4];
+  float xc[G][NU], xn[G][NU];
 #pragma unroll
   for (int g = 0; g < G; ++g)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) xc[g][u] = xn[g][u] = 0.f;
-  auto load_x = [&](int t, float (&x)[G][4]) {
+    for (int u = 0; u < NU; ++u) xc[g][u] = xn[g][u] = 0.f;
+  auto load_x = [&](int t, float (&x)[G][NU]) {
     if (own && t < lens_s[eb]) {
       const float* src = a.Xg + ((int64_t)t * B + b0 + eb) * GH + j0 + ju;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + g * H));
-        x[g][0] = v.x; x[g][1] = v.y; x[g][2] = v.z; x[g][3] = v.w;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + g * H));
+        x[g][0] = v.x; x[g][1] = v.y;
       }
     }
   };
-  PROXY_FENCE_SMEM();       // Bhi/Blo were written through the generic proxy
+  PROXY_FENCE_SMEM();       // hbuf was written through the generic proxy
   TC_FENCE_BEFORE();
   __syncthreads();
   TC_FENCE_AFTER();
   const int t_end = t_end_s;
   if (t_end > 0) load_x(0, xc);
-  // one phase of raw_full[x] = the complete h_t (16 rows x H units x 4 B) has landed from all owners
-  const uint32_t tx_bytes = (uint32_t)(TC_BT * H * 4);
+  // one phase of raw_full[x] = the h_t slices (hi + lo, 16 rows) of all the OTHER owners have landed
+  const uint32_t tx_bytes = (uint32_t)((H - nj) * 128);
   if (tid == 0) {
     mbar_arrive_expect_tx(&raw_full[0], tx_bytes);
     mbar_arrive_expect_tx(&raw_full[1], tx_bytes);
@@ -297,61 +330,65 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   cluster.sync();           // barriers initialised and armed everywhere before remote traffic
 
   const uint32_t idesc = make_idesc_tf32(128, TC_BT);
-  const uint32_t hraw_addr = smem_u32(hraw);
+  const uint32_t hbuf_addr = smem_u32(hbuf);
   const uint32_t bar_addr[2] = {smem_u32(&raw_full[0]), smem_u32(&raw_full[1])};
+  const int hoff = ((j0 + ju) >> 2) * 128 + eb * 4 + (ju & 3);   // float offset of this thread's unit pair in a buffer
 
+  TC_KSTAMP(2);
+  if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) a.dbg[512 + 5] = t_end;
+  long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last_stamp = 0;
+#define TC_STAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) { const long long now_ = clock64(); if ((i) > 0) ph[i] += now_ - last_stamp; last_stamp = now_; } } while (0)
   for (int t = 0; t < t_end; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
-    if (t + 1 < t_end) load_x(t + 1, xn);
-    const float* hprev = hraw + cur * Kp * TC_BT;
+    TC_STAMP(0);
+    const float* hprev = hbuf + cur * HB;
     if (t > 0) {
-      // h_{t-1} has landed from every CTA of the cluster; split it into the hi/lo B operand
+      // the slices of h_{t-1} owned by the other CTAs have landed (bulk copies, async proxy) next to our own
       const int use = (t - (cur == 0 ? 2 : 1)) >> 1;
       mbar_wait_cluster(&raw_full[cur], use & 1);
+      TC_STAMP(1);
       if (tid == 0) mbar_arrive_expect_tx(&raw_full[cur], tx_bytes);   // arm the next use of this buffer
-      const float4* src = reinterpret_cast<const float4*>(hprev);
-      float4* dhi = reinterpret_cast<float4*>(Bhi);
-      float4* dlo = reinterpret_cast<float4*>(Blo);
-      for (int i = tid; i < Kp * TC_BT / 4; i += TC_NT) {
-        const float4 v = src[i];
-        float4 h, l;
-        h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-        dhi[i] = h;
-        dlo[i] = l;
-      }
-      PROXY_FENCE_SMEM();
-      TC_FENCE_BEFORE();
-      __syncthreads();
       TC_FENCE_AFTER();
     }
-    if (warp == 0) {
+    TC_STAMP(2);
+    if (warp >= 4 && warp < 7) {
+      // warp 4: D1 = A_hi B_hi, warp 5: D2 = A_hi B_lo, warp 6: D3 = A_lo B_hi  (3xTF32 split, one chain per warp)
       if (elect_one_sync()) {
-        issue_3xtf32(tD, tAhi, tAlo, Bhi, Blo, KS, idesc);
+        const int c = warp - 4;
+        const uint32_t bbase = hbuf_addr + cur * HB * 4 + (c == 1 ? 256 : 0);
+        issue_chain(tD + c * TC_BT, c == 2 ? tAlo : tAhi, bbase, 512, KS, idesc, 0);
         umma_commit(&mma_done);
       }
       __syncwarp();
     }
+    TC_STAMP(3);
+    // input pre-activations of the NEXT step: in flight while the tensor core works
+    if (t + 1 < t_end) load_x(t + 1, xn);
     mbar_wait_cta(&mma_done, t & 1);
+    TC_STAMP(4);
     TC_FENCE_AFTER();
-    {
-      float v[16], w[16];
-      tmem_ld16(tD + ((uint32_t)(warp * 32) << 16), v);
-      tmem_ld16(tD + TC_BT + ((uint32_t)(warp * 32) << 16), w);
+    if (warp < 4) {
+      float v[16], w[16], x[16];
+      tmem_ld16(tD + lane_off, v);
+      tmem_ld16(tD + TC_BT + lane_off, w);
+      tmem_ld16(tD + 2 * TC_BT + lane_off, x);
 #pragma unroll
-      for (int b = 0; b < 16; ++b) gsm[b * GSM_LD + tid] = v[b] + w[b];
+      for (int b = 0; b < 16; ++b) gsm[b * GSM_LD + tid] = v[b] + (w[b] + x[b]);
     }
     TC_FENCE_BEFORE();
     __syncthreads();
+    TC_STAMP(5);
 
+    float hn[NU] = {0.f, 0.f};
+    float sv[NU][4];
+    bool active = false;
     if (own) {
-      const bool active = t < lens_s[eb];
-      const float4 hp4 = *reinterpret_cast<const float4*>(hprev + bidx(eb, j0 + ju));
-      const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
-      float hn[4];
-      float sv[4][4];
+      active = t < lens_s[eb];
+      const float2 hph = *reinterpret_cast<const float2*>(hprev + hoff);
+      const float2 hpl = *reinterpret_cast<const float2*>(hprev + hoff + 64);
+      const float hp[NU] = {hph.x + hpl.x, hph.y + hpl.y};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         const float4 p4 = *reinterpret_cast<const float4*>(gsm + eb * GSM_LD + 4 * (ju + u));
         const float pre[4] = {p4.x, p4.y, p4.z, p4.w};
         float xg[4] = {0.f, 0.f, 0.f, 0.f};
@@ -382,29 +419,50 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
           }
         }
       }
-      // publish h_t[b, j0+ju .. +3] (fp32, one 16-byte store) into every CTA of the cluster
-      const float4 hv = make_float4(hn[0], hn[1], hn[2], hn[3]);
-      const uint32_t off = hraw_addr + (uint32_t)(nxt * Kp * TC_BT + bidx(eb, j0 + ju)) * 4u;
-      for (int rr = 0; rr < C; ++rr) st_async_v4(map_to_rank(off, rr), hv, map_to_rank(bar_addr[nxt], rr));
-      if (row_ok) {
-        const int64_t row1 = (int64_t)(t + 1) * B + b0 + eb;
-        *reinterpret_cast<float4*>(a.hs + row1 * H + j0 + ju) = hv;
-        if (G == 4) *reinterpret_cast<float4*>(a.cs + row1 * H + j0 + ju) = make_float4(cst[0], cst[1], cst[2], cst[3]);
-        if (active && G > 1) {
-          float* ap = a.act + ((int64_t)t * B + b0 + eb) * 4 * H + j0 + ju;
+      // h_t pair of this thread, pre-split, into the LOCAL copy of the next buffer
+      float2 hh, hl;
+      hh.x = tf32_hi(hn[0]); hh.y = tf32_hi(hn[1]);
+      hl.x = hn[0] - hh.x; hl.y = hn[1] - hh.y;
+      *reinterpret_cast<float2*>(hbuf + nxt * HB + hoff) = hh;
+      *reinterpret_cast<float2*>(hbuf + nxt * HB + hoff + 64) = hl;
+    }
+    TC_STAMP(6);
+    // own slice complete in shared memory -> one bulk copy per peer CTA (hi and lo blocks are contiguous);
+    // lane 0 of warp w serves peer w: the C-1 copies are issued concurrently by different warps.  (Measured:
+    // the exchange is bound by the ~20 B/clk DSMEM egress of the SM; per-thread st.async of the same bytes and
+    // fp32-only st.async + receiver-side split were both slower, see DESIGN.md.)
+    PROXY_FENCE_SMEM();
+    TC_STAMP(8);
+    __syncthreads();
+    TC_STAMP(9);
+    if ((tid & 31) == 0 && nj > 0) {
+      const uint32_t src = hbuf_addr + (uint32_t)(nxt * HB + (j0 >> 2) * 128) * 4u;
+      const uint32_t bytes = (uint32_t)(nj >> 2) * 512u;
+      for (int rr = warp; rr < C; rr += FWD_NT / 32)
+        if (rr != rank) bulk_copy_to_peer(map_to_rank(src, rr), src, bytes, map_to_rank(bar_addr[nxt], rr));
+    }
+    TC_STAMP(10);
+    // saved trajectories for the backward pass: issued last so that nothing on the critical path waits on them
+    if (own && row_ok) {
+      const int64_t row1 = (int64_t)(t + 1) * B + b0 + eb;
+      *reinterpret_cast<float2*>(a.hs + row1 * H + j0 + ju) = make_float2(hn[0], hn[1]);
+      if (G == 4) *reinterpret_cast<float2*>(a.cs + row1 * H + j0 + ju) = make_float2(cst[0], cst[1]);
+      if (active && G > 1) {
+        float* ap = a.act + ((int64_t)t * B + b0 + eb) * 4 * H + j0 + ju;
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<float4*>(ap + g * H) = make_float4(sv[0][g], sv[1][g], sv[2][g], sv[3][g]);
-        }
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(ap + g * H) = make_float2(sv[0][g], sv[1][g]);
       }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) xc[g][u] = xn[g][u];
+      for (int u = 0; u < NU; ++u) xc[g][u] = xn[g][u];
+    TC_STAMP(7);
   }
 
-  // final state: wait for the last exchange so every CTA can read the full h (only own slice is written)
+  TC_KSTAMP(3);
+  if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) for (int i = 0; i < 12; ++i) a.dbg[i] = ph[i];
+  // final state: wait for the last exchange (only the own slice is written out)
   if (t_end > 0) {
     const int fin = t_end & 1;
     const int use = (t_end - (fin == 0 ? 2 : 1)) >> 1;
@@ -412,14 +470,15 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   }
   if (a.h_last && own && row_ok) {
     const int fin = t_end & 1;
-    const float4 hv = *reinterpret_cast<const float4*>(hraw + fin * Kp * TC_BT + bidx(eb, j0 + ju));
-    *reinterpret_cast<float4*>(a.h_last + (int64_t)(b0 + eb) * H + j0 + ju) = hv;
+    const float2 hh = *reinterpret_cast<const float2*>(hbuf + fin * HB + hoff);
+    const float2 hl = *reinterpret_cast<const float2*>(hbuf + fin * HB + hoff + 64);
+    *reinterpret_cast<float2*>(a.h_last + (int64_t)(b0 + eb) * H + j0 + ju) = make_float2(hh.x + hl.x, hh.y + hl.y);
   }
   TC_FENCE_BEFORE();
   cluster.sync();   // nobody exits while peers may still write to / arrive on this CTA's shared memory
+  TC_KSTAMP(4);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // backward (BPTT)
@@ -427,7 +486,7 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 // TMEM map (MT = number of 128-row tiles of the hidden index k, Kb = 4*Hs own gate columns):
 //   D1_mt at 32*mt, D2_mt at 32*mt+16; A_mt_hi at 32*MT + mt*2*Kb, A_mt_lo right after it.
 template <int G, int MT>
-__global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
@@ -440,13 +499,15 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   const int j0 = rank * Hs;
   const int nj = max(0, min(Hs, H - j0));
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int quad = warp & 3;
+  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
   extern __shared__ __align__(128) float smem[];
   float* Bhi = smem;                            // [Kb/4][16][4]  da (hi)
   float* Blo = Bhi + Kb * TC_BT;                // da (lo)
-  float* part = Blo + Kb * TC_BT;               // [2][C][16][Hs] partial dh received from the peers
-  float* dsm = part + 2 * C * TC_BT * Hs;       // [16][HP+4] partial dh of this CTA, row b, column k
-  const int DLD = HP + 4;
+  float* part = Blo + Kb * TC_BT;               // [2][C][16][Hs] partial dh received from the peers (bulk copies)
+  float* sbuf = part + 2 * C * TC_BT * Hs;      // [2][C][16][Hs] partial dh of this CTA, grouped by owner (send buffer)
+  const int PB = C * TC_BT * Hs;                // floats per part / send buffer
   __shared__ __align__(8) uint64_t part_full[2];
   __shared__ __align__(8) uint64_t mma_done;
   __shared__ uint32_t tmem_base_s;
@@ -457,15 +518,15 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   if (tid == 0) {
     mbar_init(&part_full[0], 1);
     mbar_init(&part_full[1], 1);
-    mbar_init(&mma_done, 1);
+    mbar_init(&mma_done, MT + 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < 2 * Kb * TC_BT; i += TC_NT) Bhi[i] = 0.f;            // Bhi and Blo are contiguous
-  for (int i = tid; i < 2 * C * TC_BT * Hs; i += TC_NT) part[i] = 0.f;
+  for (int i = tid; i < 2 * Kb * TC_BT; i += FWD_NT) Bhi[i] = 0.f;            // Bhi and Blo are contiguous
+  for (int i = tid; i < 4 * C * TC_BT * Hs; i += FWD_NT) part[i] = 0.f;          // part and sbuf are contiguous
   TC_FENCE_BEFORE();
   __syncthreads();
   TC_FENCE_AFTER();
@@ -477,36 +538,35 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   const uint32_t tmem = tmem_base_s;
 
   // ---- A operand tiles: row = hidden index k, column kk = 4*j + g  <->  W_hid[k][g*H + j0 + j]
+  //      warps 0-3 stage the hi copies, warps 4-7 the lo copies
   {
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const bool want_lo = warp >= 4;
     for (int mt = 0; mt < MT; ++mt) {
-      const int k = mt * 128 + tid;
+      const int k = mt * 128 + quad * 32 + (tid & 31);
       const float* src = a.W_hid + (int64_t)k * GH + j0;
-      const uint32_t tAhi = tmem + 32 * MT + mt * 2 * Kb, tAlo = tAhi + Kb;
+      const uint32_t dst = tmem + 32 * MT + mt * 2 * Kb + (want_lo ? Kb : 0) + lane_off;
       for (int c0 = 0; c0 < Kb; c0 += 8) {
-        uint32_t hi[8], lo[8];
+        uint32_t r[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int kk = c0 + i, j = kk >> 2, g = kk & 3;
           const float v = (k < H && g < G && j < nj) ? __ldg(src + g * H + j) : 0.f;
           const float h = tf32_hi(v);
-          hi[i] = __float_as_uint(h);
-          lo[i] = __float_as_uint(v - h);
+          r[i] = __float_as_uint(want_lo ? v - h : h);
         }
-        tmem_st8(tAhi + lane_off + c0, hi);
-        tmem_st8(tAlo + lane_off + c0, lo);
+        tmem_st8(dst + c0, r);
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 
-  const int eb = tid >> 3, jq = tid & 7;
-  const int ju = 4 * jq;
-  const bool own = ju < nj;
+  const int eb = tid >> 4, jq = (tid >> 1) & 7, half = tid & 1;
+  const int ju = 4 * jq + NU * half;
+  const bool own = 4 * jq < nj;
   const bool row_ok = b0 + eb < B;
-  float carry[4], dcs[4], dpe[4][3], wci[4], wcf[4], wco[4];
+  float carry[NU], dcs[NU], dpe[NU][3], wci[NU], wcf[NU], wco[NU];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < NU; ++u) {
     carry[u] = (a.dh_last && own && row_ok) ? a.dh_last[(int64_t)(b0 + eb) * H + j0 + ju + u] : 0.f;
     dcs[u] = 0.f;
     dpe[u][0] = dpe[u][1] = dpe[u][2] = 0.f;
@@ -527,24 +587,24 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     if (own && row_ok) {
       const int64_t row = (int64_t)t * B + b0 + eb;
 #pragma unroll
-      for (int g = 0; g < G; ++g) *reinterpret_cast<float4*>(a.dXg + row * GH + g * H + j0 + ju) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (G == 3) *reinterpret_cast<float4*>(a.dac + row * H + j0 + ju) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(a.dXg + row * GH + g * H + j0 + ju) = make_float2(0.f, 0.f);
+      if (G == 3) *reinterpret_cast<float2*>(a.dac + row * H + j0 + ju) = make_float2(0.f, 0.f);
     }
   }
 
   // saved tensors of a step for this thread's 4 units: [slot][unit]
   //  LSTM: i f g o c_prev c_new | GRU: r u cand a_c h_prev | Vanilla: h_new ; last slot: dhs from above
   constexpr int NSAVE = (G == 4) ? 6 : (G == 3 ? 5 : 1);
-  float sv[NSAVE + 1][4], svn[NSAVE + 1][4];
+  float sv[NSAVE + 1][NU], svn[NSAVE + 1][NU];
 #pragma unroll
   for (int s = 0; s <= NSAVE; ++s)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sv[s][u] = svn[s][u] = 0.f;
-  auto ld4f = [](const float* p, float (&d)[4]) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    for (int u = 0; u < NU; ++u) sv[s][u] = svn[s][u] = 0.f;
+  auto ld4f = [](const float* p, float (&d)[NU]) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    d[0] = v.x; d[1] = v.y;
   };
-  auto load_saved = [&](int t, float (&s)[NSAVE + 1][4]) {
+  auto load_saved = [&](int t, float (&s)[NSAVE + 1][NU]) {
     if (own && t < lens_s[eb]) {
       const int64_t row = (int64_t)t * B + b0 + eb;
       if constexpr (G == 4) {
@@ -564,8 +624,8 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   };
   if (t_end > 0) load_saved(t_end - 1, sv);
 
-  // one phase of part_full[x] = the partial dh of my Hs units has landed from all C CTAs
-  const uint32_t tx_bytes = (uint32_t)(C * TC_BT * nj * 4);
+  // one phase of part_full[x] = the partial dh blocks of my units have landed from the C-1 other CTAs
+  const uint32_t tx_bytes = (uint32_t)((C - 1) * TC_BT * Hs * 4);
   if (tid == 0) {
     mbar_arrive_expect_tx(&part_full[0], tx_bytes);
     mbar_arrive_expect_tx(&part_full[1], tx_bytes);
@@ -574,6 +634,7 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
 
   const uint32_t idesc = make_idesc_tf32(128, TC_BT);
   const uint32_t part_addr = smem_u32(part);
+  const uint32_t sbuf_addr = smem_u32(sbuf);
   const uint32_t bar_addr[2] = {smem_u32(&part_full[0]), smem_u32(&part_full[1])};
   int n_wait[2] = {0, 0};      // completed phases of each part_full barrier
 
@@ -587,19 +648,22 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
       n_wait[rpar]++;
       if (tid == 0) mbar_arrive_expect_tx(&part_full[rpar], tx_bytes);
     }
+    float dx_out[NU][4], dac_out[NU];
     if (own) {
-      float dh[4] = {carry[0], carry[1], carry[2], carry[3]};
+      float dh[NU] = {carry[0], carry[1]};
       if (t < t_end - 1) {
         for (int src = 0; src < C; ++src) {
-          const float4 p = *reinterpret_cast<const float4*>(part + ((rpar * C + src) * TC_BT + eb) * Hs + ju);
-          dh[0] += p.x; dh[1] += p.y; dh[2] += p.z; dh[3] += p.w;
+          // own contribution straight from the send buffer of step t+1, the others from the received blocks
+          const float* base = (src == rank) ? sbuf + rpar * PB : part + rpar * PB;
+          const float2 p = *reinterpret_cast<const float2*>(base + (src * TC_BT + eb) * Hs + ju);
+          dh[0] += p.x; dh[1] += p.y;
         }
       }
       const bool active = t < lens_s[eb];
       const int64_t row = (int64_t)t * B + b0 + eb;
-      float da[4][4], dx[4][4];   // [unit][gate]
+      float da[NU][4], dx[NU][4];   // [unit][gate]
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) da[u][g] = dx[u][g] = 0.f;
         float carry_new = dh[u];
@@ -653,12 +717,10 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
         *reinterpret_cast<float4*>(Bhi + (ju + u) * (TC_BT * 4) + eb * 4) = h4;
         *reinterpret_cast<float4*>(Blo + (ju + u) * (TC_BT * 4) + eb * 4) = l4;
       }
-      if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-          *reinterpret_cast<float4*>(a.dXg + row * GH + g * H + j0 + ju) = make_float4(dx[0][g], dx[1][g], dx[2][g], dx[3][g]);
-        if (G == 3) *reinterpret_cast<float4*>(a.dac + row * H + j0 + ju) = make_float4(da[0][2], da[1][2], da[2][2], da[3][2]);
-      }
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { dx_out[u][g] = dx[u][g]; dac_out[u] = da[u][2]; }
     }
     PROXY_FENCE_SMEM();
     TC_FENCE_BEFORE();
@@ -666,42 +728,66 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     TC_FENCE_AFTER();
 
     // ---- phase B: partial dh_{t-1}[b][k] = sum_kk da[b][kk] * W_hid[k][kk], all k (MT tiles of 128 rows)
-    if (warp == 0) {
+    if (warp >= 4 && warp <= 4 + MT) {
+      // warp 4: the main chains D1_mt = A_hi B_hi of every hidden tile; warp 5+mt: the correction chain
+      // D2_mt = A_hi B_lo + A_lo B_hi of tile mt  (MT + 1 instruction streams, MT + 1 commits)
       if (elect_one_sync()) {
-        for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t bhi = smem_u32(Bhi), blo = smem_u32(Blo);
+        if (warp == 4) {
+          for (int mt = 0; mt < MT; ++mt) issue_chain(tmem + 32 * mt, tmem + 32 * MT + mt * 2 * Kb, bhi, TC_BT * 16, KS, idesc, 0);
+        } else {
+          const int mt = warp - 5;
           const uint32_t tAhi = tmem + 32 * MT + mt * 2 * Kb;
-          issue_3xtf32(tmem + 32 * mt, tAhi, tAhi + Kb, Bhi, Blo, KS, idesc);
+          issue_chain(tmem + 32 * mt + 16, tAhi, blo, TC_BT * 16, KS, idesc, 0);
+          issue_chain(tmem + 32 * mt + 16, tAhi + Kb, bhi, TC_BT * 16, KS, idesc, 1);
         }
         umma_commit(&mma_done);
       }
       __syncwarp();
     }
+    // gradient wrt the input pre-activations: streamed out while the tensor core works
+    if (own && row_ok) {
+      const int64_t row = (int64_t)t * B + b0 + eb;
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        *reinterpret_cast<float2*>(a.dXg + row * GH + g * H + j0 + ju) = make_float2(dx_out[0][g], dx_out[1][g]);
+      if (G == 3) *reinterpret_cast<float2*>(a.dac + row * H + j0 + ju) = make_float2(dac_out[0], dac_out[1]);
+    }
     mbar_wait_cta(&mma_done, (t_end - 1 - t) & 1);
     TC_FENCE_AFTER();
+    {
+      // hidden tile mt is drained by warps 4*mt .. 4*mt+3 (MT == 2), or by warps 0-3 alone (MT == 1)
+      float* sb = sbuf + par * PB;
+      const int mt = warp >> 2;
+      if (mt < MT) {
+        float v[16], w[16];
+        tmem_ld16(tmem + 32 * mt + lane_off, v);
+        tmem_ld16(tmem + 32 * mt + 16 + lane_off, w);
+        const int k = mt * 128 + quad * 32 + (tid & 31);
+        if (k < H) {
+          const int rr = k / Hs, jo = k - rr * Hs;      // owner of hidden unit k and its slot there
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float v[16], w[16];
-      tmem_ld16(tmem + 32 * mt + ((uint32_t)(warp * 32) << 16), v);
-      tmem_ld16(tmem + 32 * mt + 16 + ((uint32_t)(warp * 32) << 16), w);
-#pragma unroll
-      for (int b = 0; b < 16; ++b) dsm[b * DLD + mt * 128 + tid] = v[b] + w[b];
+          for (int b = 0; b < 16; ++b) sb[(rr * TC_BT + b) * Hs + jo] = v[b] + w[b];
+        }
+      }
     }
+    // ---- phase C: reduce-scatter: one bulk copy of the [16 x Hs] block per peer, into slot [par][my rank]
+    PROXY_FENCE_SMEM();
     TC_FENCE_BEFORE();
     __syncthreads();
-
-    // ---- phase C: reduce-scatter: quad (row b, k = 4q..4q+3) goes to the owner of k, slot [par][my rank]
-    for (int i = tid; i < TC_BT * (H / 4); i += TC_NT) {
-      const int b = i / (H / 4), q = i - b * (H / 4);
-      const int k = 4 * q;
-      const int rr = k / Hs, jo = k - rr * Hs;
-      const float4 v = *reinterpret_cast<const float4*>(dsm + b * DLD + k);
-      const uint32_t off = part_addr + (uint32_t)(((par * C + rank) * TC_BT + b) * Hs + jo) * 4u;
-      st_async_v4(map_to_rank(off, rr), v, map_to_rank(bar_addr[par], rr));
+    if ((tid & 31) == 0) {
+      const uint32_t bytes = (uint32_t)(TC_BT * Hs * 4);
+      for (int rr = warp; rr < C; rr += FWD_NT / 32) {
+        if (rr == rank) continue;
+        const uint32_t src = sbuf_addr + (uint32_t)(par * PB + rr * TC_BT * Hs) * 4u;
+        const uint32_t dst = part_addr + (uint32_t)(par * PB + rank * TC_BT * Hs) * 4u;
+        bulk_copy_to_peer(map_to_rank(dst, rr), src, bytes, map_to_rank(bar_addr[par], rr));
+      }
     }
 #pragma unroll
     for (int s = 0; s <= NSAVE; ++s)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) sv[s][u] = svn[s][u];
+      for (int u = 0; u < NU; ++u) sv[s][u] = svn[s][u];
   }
 
   // ---- gradients of the learned initial states and of the peepholes
@@ -710,10 +796,10 @@ __global__ void __launch_bounds__(TC_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   }
   if (own && row_ok) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) {
       float dh = carry[u];
       if (t_end > 0)
-        for (int src = 0; src < C; ++src) dh += part[((0 * C + src) * TC_BT + eb) * Hs + ju + u];
+        for (int src = 0; src < C; ++src) dh += ((src == rank) ? sbuf : part)[(src * TC_BT + eb) * Hs + ju + u];   // buffer 0
       atomicAdd(a.g_h_init + j0 + ju + u, dh);
       if (G == 4) {
         atomicAdd(a.g_c_init + j0 + ju + u, dcs[u]);
@@ -739,7 +825,7 @@ TcPlan tc_plan(int G, int H) {
   if (getenv("SBR_DISABLE_TC")) return p;
   if (H % 4 != 0 || H < 8) return p;
   p.Kp = (int)round_up(H, 8);
-  if (32 + 2 * p.Kp > 512) return p;
+  if (64 + 2 * p.Kp > 512) return p;
   for (int C = 8; C >= 1; C >>= 1) {
     const int Hs = (int)round_up(cdiv(H, C), 4);
     if (Hs > 32) break;
@@ -751,18 +837,18 @@ TcPlan tc_plan(int G, int H) {
   // backward: MT tiles of 128 hidden rows, Kb = 4*Hs own gate columns, hi+lo: 32*MT + 2*MT*Kb TMEM columns
   p.MT = cdiv(H, 128);
   p.bwd_ok = (32 * p.MT + 2 * p.MT * 4 * p.Hs) <= 512;
-  size_t fb = (size_t)2 * 4 * p.Hs * TC_BT + (size_t)2 * p.C * TC_BT * p.Hs + (size_t)TC_BT * (p.MT * 128 + 4);
+  size_t fb = (size_t)2 * 4 * p.Hs * TC_BT + (size_t)4 * p.C * TC_BT * p.Hs;
   p.smem_bwd = std::max<size_t>(fb * sizeof(float), 120 * 1024);
   return p;
 }
 
 template <typename Kern>
-int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArgs& args) {
+int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArgs& args, int threads = TC_NT) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) { sbr_set_error(m, SBR_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SBR_E_CUDA; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.C * n_tiles, 1, 1);
-  cfg.blockDim = dim3(TC_NT, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = p.smem;
   cfg.stream = m->stream;
   cudaLaunchAttribute attr[1];
@@ -790,9 +876,33 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act; a.h_last = h_last;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   const int n_tiles = cdiv(B, TC_BT);
-  if (L.G == 4) return launch_tc(m, rnn_fwd_tc_kernel<4>, p, n_tiles, a);
-  if (L.G == 3) return launch_tc(m, rnn_fwd_tc_kernel<3>, p, n_tiles, a);
-  return launch_tc(m, rnn_fwd_tc_kernel<1>, p, n_tiles, a);
+  static long long* dbg = nullptr;
+  if (getenv("SBR_TC_TIMELINE")) {
+    if (!dbg) { cudaMalloc(&dbg, 80 * 8 * sizeof(long long)); cudaMemset(dbg, 0, 80 * 8 * sizeof(long long)); }
+    a.dbg = dbg;
+  }
+  if (L.G == 4) {
+    rc = launch_tc(m, rnn_fwd_tc_kernel<4>, p, n_tiles, a, FWD_NT);
+    if (rc == 0 && a.dbg) {
+      static int calls = 0;
+      if (++calls == 8) {
+        long long h[80 * 8];
+        cudaStreamSynchronize(m->stream);
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        double acc[12] = {0};
+        int n = (int)(h[517] > 0 ? h[517] : 1);
+        for (int i = 1; i < 12; ++i) acc[i] = (double)h[i];
+        fprintf(stderr, "[tc fwd tail] proxy_fence %.0f barrier %.0f bulk_issue %.0f stores+loop %.0f\n", acc[8] / n, acc[9] / n, acc[10] / n, acc[7] / n);
+        fprintf(stderr, "[tc fwd kernel, cycles] t_end %lld | entry->A_init_done %lld | ->loop_start %lld | loop %lld (%.0f/step) | ->exit %lld\n", h[517],
+                h[513] - h[512], h[514] - h[513], h[515] - h[514], (double)(h[515] - h[514]) / (double)(h[517] > 0 ? h[517] : 1), h[516] - h[515]);
+        fprintf(stderr, "[tc fwd timeline, cycles/step] total %.0f | wait_raw %.0f split+fence %.0f mma_issue %.0f mma_wait %.0f ldtm+bar %.0f gate+stas %.0f stg %.0f\n",
+                acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n, acc[7] / n);
+      }
+    }
+    return rc;
+  }
+  if (L.G == 3) return launch_tc(m, rnn_fwd_tc_kernel<3>, p, n_tiles, a, FWD_NT);
+  return launch_tc(m, rnn_fwd_tc_kernel<1>, p, n_tiles, a, FWD_NT);
 }
 
 int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last) {
@@ -805,7 +915,7 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   const int n_tiles = cdiv(B, TC_BT);
-#define SBR_BWD_CASE(G_, MT_) if (L.G == G_ && p.MT == MT_) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_>, p, n_tiles, a);
+#define SBR_BWD_CASE(G_, MT_) if (L.G == G_ && p.MT == MT_) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_>, p, n_tiles, a, FWD_NT);
   SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)
 #undef SBR_BWD_CASE
   return 1;
