@@ -370,10 +370,16 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+    kern = {"rnn_fwd": "rnn_fwd_tc_kernel<4>", "rnn_bwd": "rnn_bwd_tc_kernel<4,2>"}[dom] if cfg["cell"] == "LSTM" else dom
+    roofline = {"kernel": kern, "stage": dom, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "note": "fp32 FFMA cluster scan; %d strictly sequential steps per launch (latency-bound at B=%d)"
-                        % (cfg["T"], cfg["B"]),
+                "math": "3xTF32 on tcgen05 (fp32-accurate): 3 MMA passes at the TF32 rate = 1/6 of the bf16 peak per "
+                        "algorithmic FLOP",
+                "frac_of_3xtf32_peak": (achieved / (peak_tf / 6.0)) if achieved else None,
+                "note": "cluster-persistent scan: up to %d strictly sequential steps per launch on 64 of 148 SMs "
+                        "(8 clusters x 8 CTAs at B=%d); bound by the per-step latency chain (DSMEM exchange ~20 B/clk/SM, "
+                        "tcgen05 issue, gate math), not by FLOPs or HBM" % (cfg["T"], cfg["B"]),
+                "algorithmic_flops_per_launch": stage_flops[dom], "valid_steps_per_launch": mean_V,
                 "stage_ms": {k: round(v, 4) for k, v in acc.items()}}
 
     out = None
