@@ -22,14 +22,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // variant 0: LBO = k-group stride, SBO = mn-group stride (as documented for INTERLEAVE MN-major); variant 1: swapped
 template <int N>
 __global__ void __launch_bounds__(128) k(const float* A, const float* B, float* D, int K, int variant) {
-  extern __shared__ __align__(128) uint8_t raw[];
+  extern __shared__ __align__(1024) uint8_t raw[];
   float* sA = (float*)raw;              // [K/8][128/4][8][4]
   float* sB = sA + 128 * K;             // [K/8][N/4][8][4]
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 128 * K; i += 128) { const int kk = i / 128, m = i % 128; sA[(kk / 8) * (128 * 8) + (m / 4) * 32 + (kk % 8) * 4 + (m % 4)] = A[kk * 128 + m]; }
-  for (int i = tid; i < N * K; i += 128) { const int kk = i / N, n = i % N; sB[(kk / 8) * (N * 8) + (n / 4) * 32 + (kk % 8) * 4 + (n % 4)] = B[kk * N + n]; }
+  for (int i = tid; i < 128 * K; i += 128) {
+    const int kk = i / 128, m = i % 128;
+    int idx;
+    if (variant == 2) { const int row = kk % 8, chunk = (m / 4) % 8; idx = (kk / 8) * (128 * 8) + (m / 32) * 256 + row * 32 + ((chunk ^ row) * 4) + (m % 4); }
+    else if (variant == 4) idx = (kk / 4) * (128 * 4) + m * 4 + (kk % 4);
+    else idx = (kk / 8) * (128 * 8) + (m / 4) * 32 + (kk % 8) * 4 + (m % 4);
+    sA[idx] = A[kk * 128 + m];
+  }
+  for (int i = tid; i < N * K; i += 128) {
+    const int kk = i / N, n = i % N;
+    int idx;
+    if (variant == 2) { const int row = kk % 8, chunk = (n / 4) % 8; idx = (kk / 8) * (N * 8) + (n / 32) * 256 + row * 32 + ((chunk ^ row) * 4) + (n % 4); }
+    else if (variant == 3 || variant == 4) idx = (kk / 4) * (N * 4) + n * 4 + (kk % 4);     // K-major interleave [k/4][n][4]
+    else idx = (kk / 8) * (N * 8) + (n / 4) * 32 + (kk % 8) * 4 + (n % 4);
+    sB[idx] = B[kk * N + n];
+  }
   if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&tmem_s)));
@@ -42,13 +56,23 @@ __global__ void __launch_bounds__(128) k(const float* A, const float* B, float* 
   const uint32_t tmem = tmem_s;
   if (tid == 0) {
     // kind::tf32, fp32 accum, A MN-major (bit 15), B MN-major (bit 16)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((variant == 4 ? 0u : 1u) << 15) | (((variant == 3 || variant == 4) ? 0u : 1u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     for (int ks = 0; ks < K / 8; ++ks) {
       const uint32_t a_addr = smem_u32(sA) + ks * 128 * 8 * 4, b_addr = smem_u32(sB) + ks * N * 8 * 4;
       const uint32_t mn_stride = 128;               // bytes between groups of 4 mn-elements
       const uint32_t a_kstride = 128 * 8 * 4, b_kstride = N * 8 * 4;   // bytes between groups of 8 k (unused within one MMA)
       uint64_t ad, bd;
       if (variant == 0) { ad = make_desc(a_addr, a_kstride, mn_stride); bd = make_desc(b_addr, b_kstride, mn_stride); }
+      else if (variant == 2) {   // SW128: LBO = stride between 32-element MN groups (1024 B), SBO = stride between 8-row K groups
+        ad = make_desc(a_addr, 1024, a_kstride) | ((uint64_t)2 << 61);
+        bd = make_desc(b_addr, 1024, b_kstride) | ((uint64_t)2 << 61);
+      } else if (variant == 4) {
+        ad = make_desc(smem_u32(sA) + ks * 2 * (128 * 16), 128 * 16, 128);
+        bd = make_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+      } else if (variant == 3) {
+        ad = make_desc(a_addr, a_kstride, mn_stride);
+        bd = make_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+      }
       else { ad = make_desc(a_addr, mn_stride, a_kstride); bd = make_desc(b_addr, mn_stride, b_kstride); }
       mma_ss(tmem, ad, bd, idesc, ks > 0);
     }
@@ -78,7 +102,7 @@ template <int N> void run(int K, int variant) {
   CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
   CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xFF, D.size() * 4));
-  size_t smem = (size_t)(128 + N) * K * 4 + 128;
+  size_t smem = (size_t)(128 + N) * K * 4 + 2048;
   CK(cudaFuncSetAttribute(k<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<N><<<1, 128, smem>>>(dA, dB, dD, K, variant);
   CK(cudaDeviceSynchronize());
@@ -88,8 +112,8 @@ template <int N> void run(int K, int variant) {
   printf("MN-major N=%d K=%d variant=%d: max err %.3e mismatches %d  D[0..2]=%g %g %g  ref=%g %g %g  D[N]=%g ref=%g\n", N, K, variant, maxerr, bad, D[0], D[1], D[2], ref[0], ref[1], ref[2], D[N], ref[N]);
 }
 int main() {
-  run<16>(8, 0); run<16>(8, 1);
-  run<16>(32, 0); run<16>(32, 1);
-  run<160>(32, 0); run<160>(32, 1);
+  run<32>(8, 4); run<32>(32, 4); run<32>(8, 0); run<32>(8, 2); run<32>(8, 3);
+  run<32>(32, 2); run<32>(32, 3);
+  run<160>(32, 2); run<160>(32, 3);
   return 0;
 }

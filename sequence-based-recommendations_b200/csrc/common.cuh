@@ -88,6 +88,7 @@ struct sbr_model {
   cudaStream_t side = nullptr;        // off-critical-path work (see side_fork / side_join in model.cu)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool side_pending = false;
+  bool staging_in_flight = false;     // pinned staging buffers still feed an H2D copy
   std::string err;
   int err_code = 0;
   int64_t launches = 0;

@@ -199,6 +199,117 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(int M, int N, int K, cons
   }
 }
 
+// ---- tensor-core variant of the same K-slow product: warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (hi = tf32(x), lo = x - hi; a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate), fragments read straight from
+// the cp.async-filled [k][m] / [k][n] tiles (row pitch +8 floats: conflict-free).  8 warps as 2 (M) x 4 (N),
+// warp tile 64 x 32.  Operands need no transposition or descriptor; the tcgen05 version of this GEMM is the
+// round-2 item.
+constexpr int MM_BK = 16, MM_STAGES = 3, MM_PITCH = 128 + 8;
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float l = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(l));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256) sgemm_tn_mma_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                            const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                            int ldc, float alpha, int k_per_split, int accumulate) {
+  extern __shared__ __align__(16) float mm_smem[];
+  float (*As)[MM_BK][MM_PITCH] = reinterpret_cast<float (*)[MM_BK][MM_PITCH]>(mm_smem);
+  float (*Bs)[MM_BK][MM_PITCH] = reinterpret_cast<float (*)[MM_BK][MM_PITCH]>(mm_smem + MM_STAGES * MM_BK * MM_PITCH);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;       // warp tile origin inside the CTA tile
+  const int g = lane >> 2, tq = lane & 3;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const int n_tiles = (k_end - k_begin + MM_BK - 1) / MM_BK;
+
+  auto issue = [&](int tile, int stage) {
+    const int k0 = k_begin + tile * MM_BK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256;
+      const int kk = idx >> 5, c4 = (idx & 31) * 4;
+      const int gk = k0 + kk;
+      const bool kin = gk < k_end;
+      const bool ain = kin && (m0 + c4 < M);
+      const bool bin = kin && (n0 + c4 < N);
+      cp_async16(&As[stage][kk][c4], ain ? A + (int64_t)gk * lda + m0 + c4 : A, ain ? 16 : 0);
+      cp_async16(&Bs[stage][kk][c4], bin ? B + (int64_t)gk * ldb + n0 + c4 : B, bin ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+
+  for (int s2 = 0; s2 < MM_STAGES - 1; ++s2) {
+    if (s2 < n_tiles) issue(s2, s2);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    asm volatile("cp.async.wait_group %0;" :: "n"(MM_STAGES - 2) : "memory");
+    __syncthreads();
+    const int nxt = tile + MM_STAGES - 1;
+    if (nxt < n_tiles) issue(nxt, nxt % MM_STAGES);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const int st = tile % MM_STAGES;
+#pragma unroll
+    for (int k8 = 0; k8 < MM_BK; k8 += 8) {
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        split_tf32(Bs[st][k8 + tq][wn + j * 8 + g], bh[j][0], bl[j][0]);
+        split_tf32(Bs[st][k8 + tq + 4][wn + j * 8 + g], bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t ah[4], al[4];
+        const int mrow = wm + i * 16 + g;
+        split_tf32(As[st][k8 + tq][mrow], ah[0], al[0]);
+        split_tf32(As[st][k8 + tq][mrow + 8], ah[1], al[1]);
+        split_tf32(As[st][k8 + tq + 4][mrow], ah[2], al[2]);
+        split_tf32(As[st][k8 + tq + 4][mrow + 8], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mma_tf32(acc[i][j], al, bh[j]);      // small terms first
+          mma_tf32(acc[i][j], ah, bl[j]);
+          mma_tf32(acc[i][j], ah, bh[j]);
+        }
+      }
+    }
+  }
+  const bool atomic_out = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int gm = m0 + wm + i * 16 + g + (r >= 2 ? 8 : 0);
+        const int gn = n0 + wn + j * 8 + 2 * tq + (r & 1);
+        if (gm < M && gn < N) {
+          float* c = C + (int64_t)gm * ldc + gn;
+          const float v = alpha * acc[i][j][r];
+          if (atomic_out) atomicAdd(c, v);
+          else if (accumulate) *c += v;
+          else *c = v;
+        }
+      }
+}
+
 __global__ void zero_matrix_kernel(float* C, int M, int N, int ldc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
@@ -235,11 +346,23 @@ int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float
   const int accumulate = beta == 1.f ? 1 : 0;
   const bool al16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
   if (ta && !tb && al16 && M % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && K >= 64) {
+    static const bool use_ffma = getenv("SBR_GEMM_FFMA") != nullptr;
+    if (!use_ffma) {
+      const size_t smem = (size_t)2 * MM_STAGES * MM_BK * MM_PITCH * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(sgemm_tn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+      }
+      sgemm_tn_mma_kernel<<<grid, 256, smem, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
+      KERNEL_CHECK(m);
+      return 0;
+    }
     const size_t smem = (size_t)TN_STAGES * TN_BK * (BM + BN) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set2 = false;
+    if (!attr_set2) {
       cudaFuncSetAttribute(sgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = true;
+      attr_set2 = true;
     }
     sgemm_tn_kernel<<<grid, 256, smem, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
     KERNEL_CHECK(m);

@@ -480,6 +480,10 @@ static int mask_to_len(sbr_model* m, const float* mask, const int32_t* X, int B,
 }
 
 static int stage_common(sbr_model* m, BatchSlot& s, const int32_t* X, const float* mask, int B) {
+  if (m->staging_in_flight) {
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    m->staging_in_flight = false;
+  }
   if (B < 1 || B > m->B) { sbr_set_error(m, SBR_E_ARG, "B=%d outside [1,%d]", B, m->B); return SBR_E_ARG; }
   if (!X || !mask) { sbr_set_error(m, SBR_E_ARG, "null X/mask"); return SBR_E_ARG; }
   int t_max = 0;
@@ -492,13 +496,14 @@ static int stage_common(sbr_model* m, BatchSlot& s, const int32_t* X, const floa
   memcpy(m->h_stage, X, xbytes);
   CU_TRY(m, cudaMemcpyAsync(s.X, m->h_stage, xbytes, cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaMemcpyAsync(s.len, m->h_len, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
-  // h_len is reused by the next call: the copy must have left the host buffer
-  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  // the pinned staging buffers are reused by the next call: it must not start before these copies have left
+  // them.  Every path that returns a cost synchronises the stream at its end, so no extra sync is paid here.
+  m->staging_in_flight = true;
   return 0;
 }
 
-extern "C" int sbr_stage_cce(sbr_model* m, int slot, const int32_t* X, const float* mask, const int32_t* Y,
-                             const float* pop, int B) {
+static int stage_cce_impl(sbr_model* m, int slot, const int32_t* X, const float* mask, const int32_t* Y,
+                          const float* pop, int B, bool sync) {
   CHECK_STICKY(m);
   if (slot < 0 || slot >= (int)m->slots.size() || !Y || !pop) { sbr_set_error(m, SBR_E_ARG, "bad slot or null Y/pop"); return SBR_E_ARG; }
   CU_TRY(m, cudaSetDevice(m->dev));
@@ -510,8 +515,16 @@ extern "C" int sbr_stage_cce(sbr_model* m, int slot, const int32_t* X, const flo
   s.n_all = B; s.row_offset = 0;
   CU_TRY(m, cudaMemcpyAsync(s.Y, Y, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaMemcpyAsync(s.pop, pop, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  if (sync) {   // Y / pop are caller buffers: they must be consumed before the call returns
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    m->staging_in_flight = false;
+  }
   return 0;
+}
+
+extern "C" int sbr_stage_cce(sbr_model* m, int slot, const int32_t* X, const float* mask, const int32_t* Y,
+                             const float* pop, int B) {
+  return stage_cce_impl(m, slot, X, mask, Y, pop, B, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,6 +681,7 @@ static int finish_step(sbr_model* m, float* cost) {
   stage_mark(m, 9);
   if (cost || m->profiling) {
     CU_TRY(m, cudaStreamSynchronize(m->stream));
+    m->staging_in_flight = false;
     if (cost) *cost = m->h_cost[0];
     if (m->profiling)
       for (int i = 0; i < SBR_N_STAGES; ++i) cudaEventElapsedTime(&m->stage_ms[i], m->ev[i], m->ev[i + 1]);
@@ -710,8 +724,10 @@ extern "C" int sbr_train_step_cce(sbr_model* m, const int32_t* X, const float* m
   int rc;
   if ((rc = begin_step(m))) return rc;
   stage_mark(m, 0);
-  if ((rc = sbr_stage_cce(m, 0, X, mask, Y, pop, B))) return rc;
-  return step_cce(m, m->slots[0], cost);
+  // the caller's buffers stay valid until this call returns, and it returns only after the stream has drained
+  if ((rc = stage_cce_impl(m, 0, X, mask, Y, pop, B, false))) return rc;
+  float local_cost;
+  return step_cce(m, m->slots[0], cost ? cost : &local_cost);
 }
 
 extern "C" int sbr_synchronize(sbr_model* m, float* last_cost) {

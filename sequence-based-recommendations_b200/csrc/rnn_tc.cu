@@ -265,11 +265,14 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     const uint32_t dst = (want_lo ? tAlo : tAhi) + lane_off;
     for (int k0 = 0; k0 < Kp; k0 += 8) {
       uint32_t r[8];
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;      // H % 4 == 0: 16-byte loads, guarded per quad
+      if (live && k0 < H) v0 = __ldg(reinterpret_cast<const float4*>(src + k0));
+      if (live && k0 + 4 < H) v1 = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+      const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float v = (live && k0 + i < H) ? __ldg(src + k0 + i) : 0.f;
-        const float h = tf32_hi(v);
-        r[i] = __float_as_uint(want_lo ? v - h : h);
+        const float h = tf32_hi(vv[i]);
+        r[i] = __float_as_uint(want_lo ? vv[i] - h : h);
       }
       tmem_st8(dst + k0, r);
     }
@@ -545,16 +548,27 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
       const int k = mt * 128 + quad * 32 + (tid & 31);
       const float* src = a.W_hid + (int64_t)k * GH + j0;
       const uint32_t dst = tmem + 32 * MT + mt * 2 * Kb + (want_lo ? Kb : 0) + lane_off;
-      for (int c0 = 0; c0 < Kb; c0 += 8) {
-        uint32_t r[8];
+      for (int c0 = 0; c0 < Kb; c0 += 16) {                       // 4 units x 4 gates per pass
+        const int jb = c0 >> 2;
+        float4 vg[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int kk = c0 + i, j = kk >> 2, g = kk & 3;
-          const float v = (k < H && g < G && j < nj) ? __ldg(src + g * H + j) : 0.f;
-          const float h = tf32_hi(v);
-          r[i] = __float_as_uint(want_lo ? v - h : h);
+        for (int g = 0; g < 4; ++g) {
+          vg[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < H && g < G && jb < nj) vg[g] = __ldg(reinterpret_cast<const float4*>(src + g * H + jb));   // nj % 4 == 0
         }
-        tmem_st8(dst + c0, r);
+        uint32_t r0[8], r1[8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float u4[4] = {vg[g].x, vg[g].y, vg[g].z, vg[g].w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float h = tf32_hi(u4[jj]);
+            const uint32_t bits = __float_as_uint(want_lo ? u4[jj] - h : h);
+            if (jj < 2) r0[4 * jj + g] = bits; else r1[4 * (jj - 2) + g] = bits;
+          }
+        }
+        tmem_st8(dst + c0, r0);
+        if (c0 + 8 < Kb) tmem_st8(dst + c0 + 8, r1);
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
