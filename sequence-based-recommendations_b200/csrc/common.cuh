@@ -60,6 +60,12 @@ struct LayerDesc {
   float* dXg = nullptr;   // [T*B, G*H]  gradient wrt Xg (zero on masked steps)
   float* dac = nullptr;   // GRU: [T*B, H] gradient wrt the candidate's hidden pre-activation (da_c)
   float* dhs = nullptr;   // [T*B, H]   gradient arriving from the layer above (nullptr for the top layer)
+  // K-major, pre-split (hi | lo) copies written by the tcgen05 scans for the tensor-core weight-gradient GEMM:
+  //   hT[part][h/128][row/4][h%128][row%4]  (state before each step),  aT[part][col/128][row/4][col%128][row%4]  (da)
+  float* hT = nullptr;
+  float* aT = nullptr;
+  int64_t hT_part = 0, hT_tile = 0, aT_part = 0, aT_tile = 0;   // strides in floats
+  bool kmajor_valid = false;   // set by the tc backward scan of the current step
 };
 
 struct ParamView {       // one entry of the reference checkpoint list
@@ -178,6 +184,10 @@ int launch_rnn_backward(sbr_model* m, const LayerDesc& L, const int32_t* len, in
 // rnn_tc.cu (returns 1 when the tcgen05 path does not apply)
 int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last);
 int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last);
+int tc_scan_applies(int G, int H);   // 1 when both tcgen05 scans handle this layer shape
+
+// wgrad_tc.cu : dW_hid[H, G*H] += sum_rows h_prev[row]^T da[row] on tcgen05 (3xTF32) from the K-major copies
+int launch_wgrad_tc(sbr_model* m, const LayerDesc& L, int rows, float* dW, int ldw);
 
 // gemm.cu : C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (row-major, beta in {0,1})
 int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,

@@ -218,7 +218,7 @@ extern "C" void sbr_destroy(sbr_model* m) {
   if (m->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)m->nccl_comm);
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(m->params); F(m->grads); F(m->opt_a); F(m->opt_b);
-  for (LayerDesc& L : m->layers) { F(L.Xg); F(L.act); F(L.hs); F(L.cs); F(L.dXg); F(L.dac); F(L.dhs); }
+  for (LayerDesc& L : m->layers) { F(L.Xg); F(L.act); F(L.hs); F(L.cs); F(L.dXg); F(L.dac); F(L.dhs); F(L.hT); F(L.aT); }
   for (BatchSlot& s : m->slots) { F(s.X); F(s.len); F(s.Y); F(s.pop); }
   F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT);
   F(m->mY); F(m->mW); F(m->cells); F(m->Wc); F(m->dWc); F(m->bc);
@@ -273,6 +273,15 @@ static int create_impl(sbr_model* m) {
     if ((rc = dev_alloc(m, &L.dXg, TB * GH))) return rc;
     if (L.G == 3 && (rc = dev_alloc(m, &L.dac, TB * H))) return rc;
     if (li + 1 < m->layers.size() && (rc = dev_alloc(m, &L.dhs, TB * H))) return rc;
+    // K-major pre-split copies for the tensor-core weight-gradient GEMM (only where the tcgen05 scans run)
+    if (tc_scan_applies(L.G, L.H) && m->B % 16 == 0 && !getenv("SBR_DISABLE_TC") && !getenv("SBR_DISABLE_TC_WGRAD")) {
+      const size_t rq_h = (TB + B) / 4, rq_a = TB / 4;
+      const size_t mts = (H + 127) / 128, nts = (GH + 127) / 128;
+      L.hT_tile = (int64_t)rq_h * 512; L.hT_part = (int64_t)mts * L.hT_tile;
+      L.aT_tile = (int64_t)rq_a * 512; L.aT_part = (int64_t)nts * L.aT_tile;
+      if ((rc = dev_alloc(m, &L.hT, (size_t)2 * L.hT_part))) return rc;
+      if ((rc = dev_alloc(m, &L.aT, (size_t)2 * L.aT_part))) return rc;
+    }
   }
   if ((rc = dev_alloc(m, &m->WhidT, (size_t)maxHGH))) return rc;
   if (m->E > 0) {
@@ -592,8 +601,12 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
       m->side_pending = true;
       if (rc) return rc;
     }
-    // dW_hid = sum_t h_{t-1}^T da_t  : one tall-K GEMM outside the scan
-    if (L.G == 3) {
+    // dW_hid = sum_t h_{t-1}^T da_t  : one tall-K GEMM outside the scan -- on tcgen05 from the K-major copies the
+    // tc scans wrote, else the generic fp32 GEMM
+    const bool tc_wgrad = L.hT && L.aT && B % 16 == 0 && rows % 8 == 0 && rows > 0 && !getenv("SBR_DISABLE_TC_BWD");
+    if (tc_wgrad) {
+      if ((rc = launch_wgrad_tc(m, L, rows, m->grads + L.W_hid, GH))) return rc;
+    } else if (L.G == 3) {
       if ((rc = launch_gemm(m, true, false, H, 2 * H, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
       if ((rc = launch_gemm(m, true, false, H, H, rows, L.hs, H, L.dac, H, m->grads + L.W_hid + 2 * H, GH, 1.f, 1.f))) return rc;
     } else {

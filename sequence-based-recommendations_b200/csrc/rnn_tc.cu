@@ -43,6 +43,8 @@ struct TcArgs {
   float clip;
   int B, H, Hs, Kp, t_max;
   long long* dbg;   // optional phase timeline of CTA 0 / thread 0 (8 stamps per step)
+  float* hT; float* aT;                 // K-major pre-split copies for the tensor-core wgrad GEMM (may be null)
+  long long hT_part, hT_tile, aT_part, aT_tile;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -324,6 +326,20 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   TC_FENCE_AFTER();
   const int t_end = t_end_s;
   if (t_end > 0) load_x(0, xc);
+  // K-major copy of the own slice of a state block (hi and lo) for the weight-gradient GEMM: one 16-byte chunk =
+  // (part, unit, 4 consecutive rows); `blk` = index of the hs block (0 = learned init, t+1 = state after step t)
+  auto dump_hT = [&](const float* buf, int blk) {
+    if (!a.hT) return;
+    for (int c = tid; c < 2 * nj * 4; c += FWD_NT) {
+      const int part = c / (nj * 4), rem = c - part * (nj * 4), j = rem >> 2, q = rem & 3;
+      const int k = j0 + j;
+      const float* src = buf + (k >> 2) * 128 + part * 64 + (4 * q) * 4 + (k & 3);
+      const float4 v = make_float4(src[0], src[4], src[8], src[12]);
+      const long long rq = ((long long)blk * B + b0) / 4 + q;
+      *reinterpret_cast<float4*>(a.hT + part * a.hT_part + (k >> 7) * a.hT_tile + (rq * 128 + (k & 127)) * 4) = v;
+    }
+  };
+  dump_hT(hbuf, 0);
   // one phase of raw_full[x] = the h_t slices (hi + lo, 16 rows) of all the OTHER owners have landed
   const uint32_t tx_bytes = (uint32_t)((H - nj) * 128);
   if (tid == 0) {
@@ -456,6 +472,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
         for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(ap + g * H) = make_float2(sv[0][g], sv[1][g]);
       }
     }
+    dump_hT(hbuf + nxt * HB, t + 1);
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -596,7 +613,38 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   TC_FENCE_AFTER();
   const int t_end = t_end_s;
 
+  // K-major copy of da (hi | lo) for the weight-gradient GEMM.  Thread <-> (part, row quad q, unit j): it reads the
+  // 4 rows x 4 gates block of that unit with four 16-byte shared loads and writes one 16-byte chunk per gate
+  // (= 4 consecutive rows of one gate column); consecutive lanes hold consecutive units = consecutive chunks.
+  int dmp_src = -1;
+  long long dmp_dst[4] = {0, 0, 0, 0};
+  if (a.aT && tid < 2 * 4 * nj) {
+    const int part = tid / (4 * nj), rem = tid - part * (4 * nj), q = rem / nj, j = rem - q * nj;
+    dmp_src = part * (Kb * TC_BT) + j * (TC_BT * 4) + (4 * q) * 4;     // Blo follows Bhi
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = g * H + j0 + j;
+      dmp_dst[g] = part * a.aT_part + (long long)(col >> 7) * a.aT_tile + ((long long)q * 128 + (col & 127)) * 4;
+    }
+  }
+  auto dump_aT = [&](int t, bool zero) {
+    if (dmp_src < 0) return;
+    float4 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      v[r] = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(Bhi + dmp_src + r * 4);
+    const long long tb = (((long long)t * B + b0) / 4) * 512;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float4 o = g == 0 ? make_float4(v[0].x, v[1].x, v[2].x, v[3].x)
+                     : g == 1 ? make_float4(v[0].y, v[1].y, v[2].y, v[3].y)
+                     : g == 2 ? make_float4(v[0].z, v[1].z, v[2].z, v[3].z)
+                              : make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+      *reinterpret_cast<float4*>(a.aT + dmp_dst[g] + tb) = o;
+    }
+  };
   // masked tail [t_end, t_max): exactly zero gradients
+  for (int t = t_end; t < a.t_max; ++t) dump_aT(t, true);
   for (int t = t_end; t < a.t_max; ++t) {
     if (own && row_ok) {
       const int64_t row = (int64_t)t * B + b0 + eb;
@@ -759,7 +807,10 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
       }
       __syncwarp();
     }
-    // gradient wrt the input pre-activations: streamed out while the tensor core works
+    // K-major copy of this step's da for the weight-gradient GEMM and the gradient wrt the input pre-activations:
+    // streamed out while the tensor core works (right after this step's proxy fence, a full step before the next
+    // one, so no fence ever waits on these stores)
+    dump_aT(t, false);
     if (own && row_ok) {
       const int64_t row = (int64_t)t * B + b0 + eb;
 #pragma unroll
@@ -889,6 +940,7 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   a.peep = m->params + L.peep; a.h_init = m->params + L.h_init; a.c_init = m->params + L.c_init;
   a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act; a.h_last = h_last;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
+  if (L.hT && B % TC_BT == 0) { a.hT = L.hT; a.hT_part = L.hT_part; a.hT_tile = L.hT_tile; }
   const int n_tiles = cdiv(B, TC_BT);
   static long long* dbg = nullptr;
   if (getenv("SBR_TC_TIMELINE")) {
@@ -928,9 +980,15 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.dh_last = dh_last; a.dhs = dh_last ? nullptr : L.dhs; a.dXg = L.dXg; a.dac = L.dac;
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
+  if (L.aT && B % TC_BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
   const int n_tiles = cdiv(B, TC_BT);
 #define SBR_BWD_CASE(G_, MT_) if (L.G == G_ && p.MT == MT_) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_>, p, n_tiles, a, FWD_NT);
   SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)
 #undef SBR_BWD_CASE
   return 1;
+}
+
+int tc_scan_applies(int G, int H) {
+  const TcPlan p = tc_plan(G, H);
+  return (p.ok && p.bwd_ok) ? 1 : 0;
 }

@@ -97,6 +97,13 @@ def test_cce_gradients(cell, H):
     check_grads(spec, B=11, T=9)
 
 
+@pytest.mark.parametrize("cell,H,B", [("LSTM", 200, 32), ("GRU", 100, 16), ("Vanilla", 48, 48), ("LSTM", 64, 128)])
+def test_cce_gradients_tensor_core_wgrad(cell, H, B):
+    """B % 16 == 0: the tcgen05 scans also emit the K-major hi/lo copies and dW_hid comes from wgrad_tc_kernel."""
+    spec = O.Spec(n_items=211, cell=cell, layers=(H,), loss="CCE")
+    check_grads(spec, B=B, T=11, seed=12)
+
+
 @pytest.mark.parametrize("cell", ["GRU", "LSTM"])
 def test_cce_gradients_wide_layer_global_weights(cell):
     """H=512: the W_hid slice does not fit in shared memory -> global-memory weight path."""
