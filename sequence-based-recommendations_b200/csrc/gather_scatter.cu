@@ -18,6 +18,10 @@ namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// one 16-byte vector reduction (sm_90+) instead of four scalar REDs: 4x fewer atomic operations at the L2
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // one warp per (t, b) row; VEC4 requires ncols % 4 == 0 and 16B-aligned bases
 template <bool VEC4>
@@ -108,10 +112,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int32_t* __
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
               }
             }
-            atomicAdd(dst + c, s.x);
-            atomicAdd(dst + c + 1, s.y);
-            atomicAdd(dst + c + 2, s.z);
-            atomicAdd(dst + c + 3, s.w);
+            red_add_v4(dst + c, s);
           }
         } else {
           for (int c = lane; c < ncols; c += 32) {

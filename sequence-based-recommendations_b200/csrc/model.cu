@@ -612,7 +612,9 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
     } else {
       if ((rc = launch_gemm(m, true, false, H, GH, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
     }
-    if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
+    // db = sum dXg: the tcgen05 BPTT kernel accumulates it itself; the FFMA fallback needs the column sum
+    if (!(tc_scan_applies(L.G, L.H) && !getenv("SBR_DISABLE_TC") && !getenv("SBR_DISABLE_TC_BWD")))
+      if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
     if (li == 0) stage_mark(m, 6);
     if (!gather_layer) {
       const float* in;

@@ -44,6 +44,7 @@ struct TcArgs {
   int B, H, Hs, Kp, t_max;
   long long* dbg;   // optional phase timeline of CTA 0 / thread 0 (8 stamps per step)
   float* hT; float* aT;                 // K-major pre-split copies for the tensor-core wgrad GEMM (may be null)
+  float* g_b;                           // bias gradient slot (backward accumulates sum dXg itself when set)
   long long hT_part, hT_tile, aT_part, aT_tile;
 };
 
@@ -596,6 +597,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   const bool own = 4 * jq < nj;
   const bool row_ok = b0 + eb < B;
   float carry[NU], dcs[NU], dpe[NU][3], wci[NU], wcf[NU], wco[NU];
+  float dbias[NU][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // sum over steps of dXg (bias gradient)
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
     carry[u] = (a.dh_last && own && row_ok) ? a.dh_last[(int64_t)(b0 + eb) * H + j0 + ju + u] : 0.f;
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
 #pragma unroll
       for (int u = 0; u < NU; ++u)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { dx_out[u][g] = dx[u][g]; dac_out[u] = da[u][2]; }
+        for (int g = 0; g < 4; ++g) { dx_out[u][g] = dx[u][g]; dac_out[u] = da[u][2]; dbias[u][g] += dx[u][g]; }
     }
     PROXY_FENCE_SMEM();
     TC_FENCE_BEFORE();
@@ -866,6 +868,10 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
       if (t_end > 0)
         for (int src = 0; src < C; ++src) dh += ((src == rank) ? sbuf : part)[(src * TC_BT + eb) * Hs + ju + u];   // buffer 0
       atomicAdd(a.g_h_init + j0 + ju + u, dh);
+      if (a.g_b) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) atomicAdd(a.g_b + g * H + j0 + ju + u, dbias[u][g]);
+      }
       if (G == 4) {
         atomicAdd(a.g_c_init + j0 + ju + u, dcs[u]);
         atomicAdd(a.g_peep + j0 + ju + u, dpe[u][0]);
@@ -981,6 +987,7 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   if (L.aT && B % TC_BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
+  a.g_b = m->grads + L.b;
   const int n_tiles = cdiv(B, TC_BT);
 #define SBR_BWD_CASE(G_, MT_) if (L.G == G_ && p.MT == MT_) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_>, p, n_tiles, a, FWD_NT);
   SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)

@@ -171,9 +171,17 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const WgArgs a) {
       tmem_ld16(tmem + 128 + lane_off + c0, w);
       if (h < a.H) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 16; i += 4) {
           const int col = nt * 128 + c0 + i;
-          if (col < a.GH) atomicAdd(a.dW + (long long)h * a.ldw + col, v[i] + w[i]);
+          float* dst = a.dW + (long long)h * a.ldw + col;
+          if (col + 3 < a.GH && (a.ldw & 3) == 0) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                         :: "l"(dst), "f"(v[i] + w[i]), "f"(v[i + 1] + w[i + 1]), "f"(v[i + 2] + w[i + 2]), "f"(v[i + 3] + w[i + 3]) : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < a.GH) atomicAdd(dst + e, v[i + e] + w[i + e]);
+          }
         }
       }
     }
