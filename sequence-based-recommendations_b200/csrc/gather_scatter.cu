@@ -67,66 +67,71 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int32_t* __restrict__ X,
                                                                 const int32_t* __restrict__ len,
                                                                 const float* __restrict__ dOut, float* __restrict__ dW,
-                                                                int B, int T, int K, int ncols, int n_rows) {
+                                                                int B, int T, int K, int ncols, int n_rows,
+                                                                int n_chunks) {
+  // one warp = 32 consecutive (t, b) rows x one 128-column chunk (VEC4) / 32-column chunk.  Runs of equal ids
+  // (nested-prefix batches put the same item in the whole warp) are summed in registers and leave as ONE reduction;
+  // distinct ids leave as independent load -> RED pairs, eight loads in flight per lane.
   const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int n_groups = (n_rows + 31) / 32;
-  for (int grp = blockIdx.x * warps_per_block + (threadIdx.x >> 5); grp < n_groups; grp += gridDim.x * warps_per_block) {
-    const int e = grp * 32 + lane;
-    int t = 0, b = 0;
-    bool valid = e < n_rows;
-    if (valid) {
-      t = e / B;
-      b = e - t * B;
-      valid = t < len[b];
-    }
-    for (int k = 0; k < K; ++k) {
-      // invalid lanes get distinct negative keys so they never join a group
-      const int id = valid ? X[((int64_t)b * T + t) * K + k] : -1 - lane;
-      const unsigned peers = __match_any_sync(0xffffffffu, id);
-      const bool leader = valid && (__ffs(peers) - 1 == lane);
-      unsigned leaders = __ballot_sync(0xffffffffu, leader);
-      while (leaders) {
-        const int L = __ffs(leaders) - 1;
-        leaders &= leaders - 1;
-        const unsigned members = __shfl_sync(0xffffffffu, peers, L);
-        const int rid = __shfl_sync(0xffffffffu, id, L);
-        float* dst = dW + (int64_t)rid * ncols;
-        const float* src0 = dOut + (int64_t)grp * 32 * ncols;
-        if (VEC4) {
-          for (int c = lane * 4; c < ncols; c += 128) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (members == 0xffffffffu) {
-              // common case (nested prefixes): the whole warp shares the id -> 32 independent loads
-#pragma unroll 8
-              for (int mlane = 0; mlane < 32; ++mlane) {
-                const float4 v = ld4(src0 + (int64_t)mlane * ncols + c);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-              }
-            } else {
-              unsigned mm = members;
-              while (mm) {
-                const int mlane = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const float4 v = ld4(src0 + (int64_t)mlane * ncols + c);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-              }
-            }
-            red_add_v4(dst + c, s);
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int grp = w / n_chunks;
+  if (grp * 32 >= n_rows) return;
+  const int chunk = w - grp * n_chunks;
+  const int e = grp * 32 + lane;
+  int t = 0, b = 0;
+  bool valid = e < n_rows;
+  if (valid) {
+    t = e / B;
+    b = e - t * B;
+    valid = t < len[b];
+  }
+  const float* src0 = dOut + (int64_t)grp * 32 * ncols;
+  for (int k = 0; k < K; ++k) {
+    const int id = valid ? X[((int64_t)b * T + t) * K + k] : -1;
+    if (VEC4) {
+      const int c = chunk * 128 + lane * 4;
+      const bool act = c < ncols;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cur = -1;
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float4 v[8];
+        int rid[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rid[i] = __shfl_sync(0xffffffffu, id, r0 + i);
+          v[i] = (rid[i] >= 0 && act) ? __ldg(reinterpret_cast<const float4*>(src0 + (int64_t)(r0 + i) * ncols + c))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (rid[i] < 0) continue;
+          if (rid[i] != cur) {
+            if (cur >= 0 && act) red_add_v4(dW + (int64_t)cur * ncols + c, s);
+            s = make_float4(0.f, 0.f, 0.f, 0.f);
+            cur = rid[i];
           }
-        } else {
-          for (int c = lane; c < ncols; c += 32) {
-            float s = 0.f;
-            unsigned mm = members;
-            while (mm) {
-              const int mlane = __ffs(mm) - 1;
-              mm &= mm - 1;
-              s += src0[(int64_t)mlane * ncols + c];
-            }
-            atomicAdd(dst + c, s);
-          }
+          s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w;
         }
       }
+      if (cur >= 0 && act) red_add_v4(dW + (int64_t)cur * ncols + c, s);
+    } else {
+      const int c = chunk * 32 + lane;
+      const bool act = c < ncols;
+      float s = 0.f;
+      int cur = -1;
+      for (int r = 0; r < 32; ++r) {
+        const int rid = __shfl_sync(0xffffffffu, id, r);
+        if (rid < 0) continue;
+        const float v = act ? src0[(int64_t)r * ncols + c] : 0.f;
+        if (rid != cur) {
+          if (cur >= 0 && act) atomicAdd(dW + (int64_t)cur * ncols + c, s);
+          s = 0.f;
+          cur = rid;
+        }
+        s += v;
+      }
+      if (cur >= 0 && act) atomicAdd(dW + (int64_t)cur * ncols + c, s);
     }
   }
 }
@@ -247,13 +252,14 @@ int launch_scatter_add_rows(sbr_model* m, const int32_t* X, const int32_t* len, 
   const int n_rows = t_max * B;
   if (n_rows == 0) return 0;
   const int wpb = 8;
-  int grid = cdiv(cdiv(n_rows, 32), wpb);
-  grid = std::min(grid, m->n_sm * 16);
   const bool v4 = (ncols % 4 == 0) && aligned16(dOut) && aligned16(dW);
+  const int n_chunks = cdiv(ncols, v4 ? 128 : 32);
+  const long long warps = (long long)cdiv(n_rows, 32) * n_chunks;
+  const int grid = (int)((warps + wpb - 1) / wpb);
   if (v4)
-    scatter_add_rows_kernel<true><<<grid, wpb * 32, 0, m->stream>>>(X, len, dOut, dW, B, T, K, ncols, n_rows);
+    scatter_add_rows_kernel<true><<<grid, wpb * 32, 0, m->stream>>>(X, len, dOut, dW, B, T, K, ncols, n_rows, n_chunks);
   else
-    scatter_add_rows_kernel<false><<<grid, wpb * 32, 0, m->stream>>>(X, len, dOut, dW, B, T, K, ncols, n_rows);
+    scatter_add_rows_kernel<false><<<grid, wpb * 32, 0, m->stream>>>(X, len, dOut, dW, B, T, K, ncols, n_rows, n_chunks);
   KERNEL_CHECK(m);
   return 0;
 }
