@@ -32,7 +32,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int TC_NT = 128;   // 4 warps: TMEM lane quadrants 0..3
-constexpr int TC_BT = 16;    // batch rows per cluster tile = MMA N
+constexpr int TC_N = 16;     // MMA N (minimum for M = 128); the cluster tile holds BT = 16 or 8 live batch rows
 constexpr int GSM_LD = 132;  // padded row of the gate staging buffer
 
 struct TcArgs {
@@ -144,8 +144,28 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&r)[8]) 
 #define TC_FENCE_AFTER() asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
 #define PROXY_FENCE_SMEM() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
 
-// B-operand layout of a [16 rows] x [Kp] matrix: float index of element (row b, k)
-__device__ __forceinline__ int bidx(int b, int k) { return (k >> 2) * (TC_BT * 4) + b * 4 + (k & 3); }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int N> __device__ __forceinline__ void tmem_ldn(uint32_t addr, float (&v)[N]) {
+  if constexpr (N == 16) tmem_ld16(addr, v); else tmem_ld8(addr, v);
+}
+// NU consecutive floats (NU = 1 or 2) as one access
+template <int N> __device__ __forceinline__ void ldn(const float* p, float (&d)[N]) {
+  if constexpr (N == 2) { const float2 v = *reinterpret_cast<const float2*>(p); d[0] = v.x; d[1] = v.y; } else d[0] = *p;
+}
+template <int N> __device__ __forceinline__ void ldgn(const float* p, float (&d)[N]) {
+  if constexpr (N == 2) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); d[0] = v.x; d[1] = v.y; } else d[0] = __ldg(p);
+}
+template <int N> __device__ __forceinline__ void stn(float* p, const float (&d)[N]) {
+  if constexpr (N == 2) *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]); else *p = d[0];
+}
 
 // 3xTF32: D1[128x16] = A_hi*B_hi ; D2[128x16] = A_hi*B_lo + A_lo*B_hi over KS k-chunks of 8.  The
 // accumulator add of the tensor core truncates, so the large term and the 2^-11-times-smaller
@@ -166,35 +186,22 @@ __device__ __forceinline__ void issue_chain(uint32_t tD, uint32_t tA, uint32_t b
   }
 }
 
-__device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tAhi, uint32_t tAlo, uint32_t bhi_addr, uint32_t blo_addr,
-                                             uint32_t lbo_bytes, int KS, uint32_t idesc) {
-  // descriptors advance by a constant per k-chunk: 2 core-matrix columns = 2 * LBO bytes
-  uint64_t dhi = make_desc(bhi_addr, lbo_bytes, 128);
-  uint64_t dlo = make_desc(blo_addr, lbo_bytes, 128);
-  const uint64_t adv = (uint64_t)(2 * lbo_bytes) >> 4;
-  mma_ts(tD, tAhi, dhi, idesc, 0);
-  mma_ts(tD + TC_BT, tAhi, dlo, idesc, 0);
-  mma_ts(tD + TC_BT, tAlo, dhi, idesc, 1);
-#pragma unroll 1
-  for (int ks = 1; ks < KS; ++ks) {
-    dhi += adv;
-    dlo += adv;
-    tAhi += 8;
-    tAlo += 8;
-    mma_ts(tD, tAhi, dhi, idesc, 1);
-    mma_ts(tD + TC_BT, tAhi, dlo, idesc, 1);
-    mma_ts(tD + TC_BT, tAlo, dhi, idesc, 1);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 constexpr int FWD_NT = 256;  // forward: 8 warps (warp w reaches TMEM lane quadrant w % 4)
-constexpr int NU = 2;        // hidden units per thread in the forward gate math
 
-template <int G>
+// BT = live batch rows of the cluster tile.  The MMA is always N = 16; with BT = 8 the B operand keeps only 8 rows
+// per core-matrix column and the descriptor's second 8-row group aliases the neighbouring block (its accumulator
+// columns are never read), so the exchange moves half the bytes, every thread owns ONE unit of the gate math, and a
+// batch of 128 rows spreads over 16 clusters = 128 SMs instead of 64.
+template <int G, int BT>
 __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
+  constexpr int TC_BT = BT;
+  constexpr int TPR = FWD_NT / BT;     // threads per batch row
+  constexpr int NU = 32 / TPR;         // hidden units per thread (Hs <= 32)
+  constexpr int KCB = BT * 8;          // floats per 4-wide k block of the B operand: hi[BT][4] | lo[BT][4]
+  constexpr int QB = BT / 4;           // row quads per tile
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
@@ -239,10 +246,10 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     const int k = kc * 4 + (rem & 3);
     const float v = k < H ? a.h_init[k] : 0.f;
     const float hi = tf32_hi(v);
-    hbuf[kc * 128 + rem] = hi;
-    hbuf[kc * 128 + 64 + rem] = v - hi;
-    hbuf[HB + kc * 128 + rem] = 0.f;
-    hbuf[HB + kc * 128 + 64 + rem] = 0.f;
+    hbuf[kc * KCB + rem] = hi;
+    hbuf[kc * KCB + BT * 4 + rem] = v - hi;
+    hbuf[HB + kc * KCB + rem] = 0.f;
+    hbuf[HB + kc * KCB + BT * 4 + rem] = 0.f;
   }
   TC_FENCE_BEFORE();
   __syncthreads();
@@ -283,10 +290,10 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   }
 
   TC_KSTAMP(1);
-  // ---- gate-math ownership: row eb, units ju, ju+1 of the slice (two threads share one 16-byte quad)
-  const int eb = tid >> 4, jq = (tid >> 1) & 7, half = tid & 1;
-  const int ju = 4 * jq + NU * half;
-  const bool own = 4 * jq < nj;                   // nj is a multiple of 4 (H % 4 == 0, Hs % 4 == 0)
+  // ---- gate-math ownership: row eb, units ju .. ju+NU-1 of the slice
+  const int eb = tid / TPR;
+  const int ju = NU * (tid % TPR);
+  const bool own = ju < nj;                       // nj is a multiple of 4 (H % 4 == 0, Hs % 4 == 0)
   const bool row_ok = b0 + eb < B;
   float cst[NU], wci[NU], wcf[NU], wco[NU];
 #pragma unroll
@@ -315,10 +322,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     if (own && t < lens_s[eb]) {
       const float* src = a.Xg + ((int64_t)t * B + b0 + eb) * GH + j0 + ju;
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(src + g * H));
-        x[g][0] = v.x; x[g][1] = v.y;
-      }
+      for (int g = 0; g < G; ++g) ldgn<NU>(src + g * H, x[g]);
     }
   };
   PROXY_FENCE_SMEM();       // hbuf was written through the generic proxy
@@ -331,28 +335,28 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   // (part, unit, 4 consecutive rows); `blk` = index of the hs block (0 = learned init, t+1 = state after step t)
   auto dump_hT = [&](const float* buf, int blk) {
     if (!a.hT) return;
-    for (int c = tid; c < 2 * nj * 4; c += FWD_NT) {
-      const int part = c / (nj * 4), rem = c - part * (nj * 4), j = rem >> 2, q = rem & 3;
+    for (int c = tid; c < 2 * nj * QB; c += FWD_NT) {
+      const int part = c / (nj * QB), rem = c - part * (nj * QB), j = rem / QB, q = rem - j * QB;
       const int k = j0 + j;
-      const float* src = buf + (k >> 2) * 128 + part * 64 + (4 * q) * 4 + (k & 3);
+      const float* src = buf + (k >> 2) * KCB + part * (BT * 4) + (4 * q) * 4 + (k & 3);
       const float4 v = make_float4(src[0], src[4], src[8], src[12]);
       const long long rq = ((long long)blk * B + b0) / 4 + q;
       *reinterpret_cast<float4*>(a.hT + part * a.hT_part + (k >> 7) * a.hT_tile + (rq * 128 + (k & 127)) * 4) = v;
     }
   };
   dump_hT(hbuf, 0);
-  // one phase of raw_full[x] = the h_t slices (hi + lo, 16 rows) of all the OTHER owners have landed
-  const uint32_t tx_bytes = (uint32_t)((H - nj) * 128);
+  // one phase of raw_full[x] = the h_t slices (hi + lo, BT rows) of all the OTHER owners have landed
+  const uint32_t tx_bytes = (uint32_t)((H - nj) * BT * 8);
   if (tid == 0) {
     mbar_arrive_expect_tx(&raw_full[0], tx_bytes);
     mbar_arrive_expect_tx(&raw_full[1], tx_bytes);
   }
   cluster.sync();           // barriers initialised and armed everywhere before remote traffic
 
-  const uint32_t idesc = make_idesc_tf32(128, TC_BT);
+  const uint32_t idesc = make_idesc_tf32(128, TC_N);
   const uint32_t hbuf_addr = smem_u32(hbuf);
   const uint32_t bar_addr[2] = {smem_u32(&raw_full[0]), smem_u32(&raw_full[1])};
-  const int hoff = ((j0 + ju) >> 2) * 128 + eb * 4 + (ju & 3);   // float offset of this thread's unit pair in a buffer
+  const int hoff = ((j0 + ju) >> 2) * KCB + eb * 4 + (ju & 3);   // float offset of this thread's units in a buffer
 
   TC_KSTAMP(2);
   if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) a.dbg[512 + 5] = t_end;
@@ -375,8 +379,8 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
       // warp 4: D1 = A_hi B_hi, warp 5: D2 = A_hi B_lo, warp 6: D3 = A_lo B_hi  (3xTF32 split, one chain per warp)
       if (elect_one_sync()) {
         const int c = warp - 4;
-        const uint32_t bbase = hbuf_addr + cur * HB * 4 + (c == 1 ? 256 : 0);
-        issue_chain(tD + c * TC_BT, c == 2 ? tAlo : tAhi, bbase, 512, KS, idesc, 0);
+        const uint32_t bbase = hbuf_addr + cur * HB * 4 + (c == 1 ? BT * 16 : 0);
+        issue_chain(tD + c * TC_N, c == 2 ? tAlo : tAhi, bbase, KCB * 4, KS, idesc, 0);
         umma_commit(&mma_done);
       }
       __syncwarp();
@@ -388,25 +392,29 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     TC_STAMP(4);
     TC_FENCE_AFTER();
     if (warp < 4) {
-      float v[16], w[16], x[16];
-      tmem_ld16(tD + lane_off, v);
-      tmem_ld16(tD + TC_BT + lane_off, w);
-      tmem_ld16(tD + 2 * TC_BT + lane_off, x);
+      float v[BT], w[BT], x[BT];
+      tmem_ldn<BT>(tD + lane_off, v);
+      tmem_ldn<BT>(tD + TC_N + lane_off, w);
+      tmem_ldn<BT>(tD + 2 * TC_N + lane_off, x);
 #pragma unroll
-      for (int b = 0; b < 16; ++b) gsm[b * GSM_LD + tid] = v[b] + (w[b] + x[b]);
+      for (int b = 0; b < BT; ++b) gsm[b * GSM_LD + tid] = v[b] + (w[b] + x[b]);
     }
     TC_FENCE_BEFORE();
     __syncthreads();
     TC_STAMP(5);
 
-    float hn[NU] = {0.f, 0.f};
+    float hn[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) hn[u] = 0.f;
     float sv[NU][4];
     bool active = false;
     if (own) {
       active = t < lens_s[eb];
-      const float2 hph = *reinterpret_cast<const float2*>(hprev + hoff);
-      const float2 hpl = *reinterpret_cast<const float2*>(hprev + hoff + 64);
-      const float hp[NU] = {hph.x + hpl.x, hph.y + hpl.y};
+      float hph[NU], hpl[NU], hp[NU];
+      ldn<NU>(hprev + hoff, hph);
+      ldn<NU>(hprev + hoff + BT * 4, hpl);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) hp[u] = hph[u] + hpl[u];
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         const float4 p4 = *reinterpret_cast<const float4*>(gsm + eb * GSM_LD + 4 * (ju + u));
@@ -440,11 +448,11 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
         }
       }
       // h_t pair of this thread, pre-split, into the LOCAL copy of the next buffer
-      float2 hh, hl;
-      hh.x = tf32_hi(hn[0]); hh.y = tf32_hi(hn[1]);
-      hl.x = hn[0] - hh.x; hl.y = hn[1] - hh.y;
-      *reinterpret_cast<float2*>(hbuf + nxt * HB + hoff) = hh;
-      *reinterpret_cast<float2*>(hbuf + nxt * HB + hoff + 64) = hl;
+      float hh[NU], hl[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) { hh[u] = tf32_hi(hn[u]); hl[u] = hn[u] - hh[u]; }
+      stn<NU>(hbuf + nxt * HB + hoff, hh);
+      stn<NU>(hbuf + nxt * HB + hoff + BT * 4, hl);
     }
     TC_STAMP(6);
     // own slice complete in shared memory -> one bulk copy per peer CTA (hi and lo blocks are contiguous);
@@ -456,8 +464,8 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     __syncthreads();
     TC_STAMP(9);
     if ((tid & 31) == 0 && nj > 0) {
-      const uint32_t src = hbuf_addr + (uint32_t)(nxt * HB + (j0 >> 2) * 128) * 4u;
-      const uint32_t bytes = (uint32_t)(nj >> 2) * 512u;
+      const uint32_t src = hbuf_addr + (uint32_t)(nxt * HB + (j0 >> 2) * KCB) * 4u;
+      const uint32_t bytes = (uint32_t)(nj >> 2) * (uint32_t)(KCB * 4);
       for (int rr = warp; rr < C; rr += FWD_NT / 32)
         if (rr != rank) bulk_copy_to_peer(map_to_rank(src, rr), src, bytes, map_to_rank(bar_addr[nxt], rr));
     }
@@ -465,12 +473,17 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     // saved trajectories for the backward pass: issued last so that nothing on the critical path waits on them
     if (own && row_ok) {
       const int64_t row1 = (int64_t)(t + 1) * B + b0 + eb;
-      *reinterpret_cast<float2*>(a.hs + row1 * H + j0 + ju) = make_float2(hn[0], hn[1]);
-      if (G == 4) *reinterpret_cast<float2*>(a.cs + row1 * H + j0 + ju) = make_float2(cst[0], cst[1]);
+      stn<NU>(a.hs + row1 * H + j0 + ju, hn);
+      if (G == 4) stn<NU>(a.cs + row1 * H + j0 + ju, cst);
       if (active && G > 1) {
         float* ap = a.act + ((int64_t)t * B + b0 + eb) * 4 * H + j0 + ju;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(ap + g * H) = make_float2(sv[0][g], sv[1][g]);
+        for (int g = 0; g < 4; ++g) {
+          float o[NU];
+#pragma unroll
+          for (int u = 0; u < NU; ++u) o[u] = sv[u][g];
+          stn<NU>(ap + g * H, o);
+        }
       }
     }
     dump_hT(hbuf + nxt * HB, t + 1);
@@ -491,9 +504,12 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   }
   if (a.h_last && own && row_ok) {
     const int fin = t_end & 1;
-    const float2 hh = *reinterpret_cast<const float2*>(hbuf + fin * HB + hoff);
-    const float2 hl = *reinterpret_cast<const float2*>(hbuf + fin * HB + hoff + 64);
-    *reinterpret_cast<float2*>(a.h_last + (int64_t)(b0 + eb) * H + j0 + ju) = make_float2(hh.x + hl.x, hh.y + hl.y);
+    float hh[NU], hl[NU];
+    ldn<NU>(hbuf + fin * HB + hoff, hh);
+    ldn<NU>(hbuf + fin * HB + hoff + BT * 4, hl);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) hh[u] += hl[u];
+    stn<NU>(a.h_last + (int64_t)(b0 + eb) * H + j0 + ju, hh);
   }
   TC_FENCE_BEFORE();
   cluster.sync();   // nobody exits while peers may still write to / arrive on this CTA's shared memory
@@ -506,8 +522,12 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 // ------------------------------------------------------------------------------------------------
 // TMEM map (MT = number of 128-row tiles of the hidden index k, Kb = 4*Hs own gate columns):
 //   D1_mt at 32*mt, D2_mt at 32*mt+16; A_mt_hi at 32*MT + mt*2*Kb, A_mt_lo right after it.
-template <int G, int MT>
+template <int G, int MT, int BT>
 __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
+  constexpr int TC_BT = BT;
+  constexpr int TPR = FWD_NT / BT;
+  constexpr int NU = 32 / TPR;
+  constexpr int QB = BT / 4;
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
@@ -592,14 +612,15 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 
-  const int eb = tid >> 4, jq = (tid >> 1) & 7, half = tid & 1;
-  const int ju = 4 * jq + NU * half;
-  const bool own = 4 * jq < nj;
+  const int eb = tid / TPR;
+  const int ju = NU * (tid % TPR);
+  const bool own = ju < nj;
   const bool row_ok = b0 + eb < B;
   float carry[NU], dcs[NU], dpe[NU][3], wci[NU], wcf[NU], wco[NU];
-  float dbias[NU][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // sum over steps of dXg (bias gradient)
+  float dbias[NU][4];                                                   // sum over steps of dXg (bias gradient)
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
+    dbias[u][0] = dbias[u][1] = dbias[u][2] = dbias[u][3] = 0.f;
     carry[u] = (a.dh_last && own && row_ok) ? a.dh_last[(int64_t)(b0 + eb) * H + j0 + ju + u] : 0.f;
     dcs[u] = 0.f;
     dpe[u][0] = dpe[u][1] = dpe[u][2] = 0.f;
@@ -620,8 +641,8 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   // (= 4 consecutive rows of one gate column); consecutive lanes hold consecutive units = consecutive chunks.
   int dmp_src = -1;
   long long dmp_dst[4] = {0, 0, 0, 0};
-  if (a.aT && tid < 2 * 4 * nj) {
-    const int part = tid / (4 * nj), rem = tid - part * (4 * nj), q = rem / nj, j = rem - q * nj;
+  if (a.aT && tid < 2 * QB * nj) {
+    const int part = tid / (QB * nj), rem = tid - part * (QB * nj), q = rem / nj, j = rem - q * nj;
     dmp_src = part * (Kb * TC_BT) + j * (TC_BT * 4) + (4 * q) * 4;     // Blo follows Bhi
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -651,8 +672,12 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     if (own && row_ok) {
       const int64_t row = (int64_t)t * B + b0 + eb;
 #pragma unroll
-      for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(a.dXg + row * GH + g * H + j0 + ju) = make_float2(0.f, 0.f);
-      if (G == 3) *reinterpret_cast<float2*>(a.dac + row * H + j0 + ju) = make_float2(0.f, 0.f);
+      float z[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) z[u] = 0.f;
+#pragma unroll
+      for (int g = 0; g < G; ++g) stn<NU>(a.dXg + row * GH + g * H + j0 + ju, z);
+      if (G == 3) stn<NU>(a.dac + row * H + j0 + ju, z);
     }
   }
 
@@ -664,10 +689,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   for (int s = 0; s <= NSAVE; ++s)
 #pragma unroll
     for (int u = 0; u < NU; ++u) sv[s][u] = svn[s][u] = 0.f;
-  auto ld4f = [](const float* p, float (&d)[NU]) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-    d[0] = v.x; d[1] = v.y;
-  };
+  auto ld4f = [](const float* p, float (&d)[NU]) { ldgn<NU>(p, d); };
   auto load_saved = [&](int t, float (&s)[NSAVE + 1][NU]) {
     if (own && t < lens_s[eb]) {
       const int64_t row = (int64_t)t * B + b0 + eb;
@@ -696,14 +718,18 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   }
   cluster.sync();
 
-  const uint32_t idesc = make_idesc_tf32(128, TC_BT);
+  const uint32_t idesc = make_idesc_tf32(128, TC_N);
   const uint32_t part_addr = smem_u32(part);
   const uint32_t sbuf_addr = smem_u32(sbuf);
   const uint32_t bar_addr[2] = {smem_u32(&part_full[0]), smem_u32(&part_full[1])};
   int n_wait[2] = {0, 0};      // completed phases of each part_full barrier
 
+  long long bph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, blast = 0;
+#define TC_BSTAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) { const long long now_ = clock64(); if ((i) > 0) bph[i] += now_ - blast; blast = now_; } } while (0)
+  const long long bstart = a.dbg ? clock64() : 0;
   for (int t = t_end - 1; t >= 0; --t) {
     const int par = t & 1, rpar = par ^ 1;
+    TC_BSTAMP(0);
     if (t > 0) load_saved(t - 1, svn);
 
     // ---- phase A: dh_t = carry + partials of step t+1 (+ gradient from the layer above); gate gradients
@@ -712,15 +738,20 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
       n_wait[rpar]++;
       if (tid == 0) mbar_arrive_expect_tx(&part_full[rpar], tx_bytes);
     }
+    TC_BSTAMP(1);
     float dx_out[NU][4], dac_out[NU];
     if (own) {
-      float dh[NU] = {carry[0], carry[1]};
+      float dh[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) dh[u] = carry[u];
       if (t < t_end - 1) {
         for (int src = 0; src < C; ++src) {
           // own contribution straight from the send buffer of step t+1, the others from the received blocks
           const float* base = (src == rank) ? sbuf + rpar * PB : part + rpar * PB;
-          const float2 p = *reinterpret_cast<const float2*>(base + (src * TC_BT + eb) * Hs + ju);
-          dh[0] += p.x; dh[1] += p.y;
+          float p[NU];
+          ldn<NU>(base + (src * TC_BT + eb) * Hs + ju, p);
+#pragma unroll
+          for (int u = 0; u < NU; ++u) dh[u] += p[u];
         }
       }
       const bool active = t < lens_s[eb];
@@ -786,10 +817,13 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) { dx_out[u][g] = dx[u][g]; dac_out[u] = da[u][2]; dbias[u][g] += dx[u][g]; }
     }
+    TC_BSTAMP(2);
     PROXY_FENCE_SMEM();
+    TC_BSTAMP(3);
     TC_FENCE_BEFORE();
     __syncthreads();
     TC_FENCE_AFTER();
+    TC_BSTAMP(4);
 
     // ---- phase B: partial dh_{t-1}[b][k] = sum_kk da[b][kk] * W_hid[k][kk], all k (MT tiles of 128 rows)
     if (warp >= 4 && warp <= 4 + MT) {
@@ -816,32 +850,41 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     if (own && row_ok) {
       const int64_t row = (int64_t)t * B + b0 + eb;
 #pragma unroll
-      for (int g = 0; g < G; ++g)
-        *reinterpret_cast<float2*>(a.dXg + row * GH + g * H + j0 + ju) = make_float2(dx_out[0][g], dx_out[1][g]);
-      if (G == 3) *reinterpret_cast<float2*>(a.dac + row * H + j0 + ju) = make_float2(dac_out[0], dac_out[1]);
+      for (int g = 0; g < G; ++g) {
+        float o[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) o[u] = dx_out[u][g];
+        stn<NU>(a.dXg + row * GH + g * H + j0 + ju, o);
+      }
+      if (G == 3) stn<NU>(a.dac + row * H + j0 + ju, dac_out);
     }
+    TC_BSTAMP(5);
     mbar_wait_cta(&mma_done, (t_end - 1 - t) & 1);
     TC_FENCE_AFTER();
+    TC_BSTAMP(6);
     {
       // hidden tile mt is drained by warps 4*mt .. 4*mt+3 (MT == 2), or by warps 0-3 alone (MT == 1)
       float* sb = sbuf + par * PB;
       const int mt = warp >> 2;
       if (mt < MT) {
-        float v[16], w[16];
-        tmem_ld16(tmem + 32 * mt + lane_off, v);
-        tmem_ld16(tmem + 32 * mt + 16 + lane_off, w);
+        float v[BT], w[BT];
+        tmem_ldn<BT>(tmem + 32 * mt + lane_off, v);
+        tmem_ldn<BT>(tmem + 32 * mt + 16 + lane_off, w);
         const int k = mt * 128 + quad * 32 + (tid & 31);
         if (k < H) {
           const int rr = k / Hs, jo = k - rr * Hs;      // owner of hidden unit k and its slot there
 #pragma unroll
-          for (int b = 0; b < 16; ++b) sb[(rr * TC_BT + b) * Hs + jo] = v[b] + w[b];
+          for (int b = 0; b < BT; ++b) sb[(rr * TC_BT + b) * Hs + jo] = v[b] + w[b];
         }
       }
     }
-    // ---- phase C: reduce-scatter: one bulk copy of the [16 x Hs] block per peer, into slot [par][my rank]
+    // ---- phase C: reduce-scatter: one bulk copy of the [BT x Hs] block per peer, into slot [par][my rank]
+    TC_BSTAMP(7);
     PROXY_FENCE_SMEM();
+    TC_BSTAMP(8);
     TC_FENCE_BEFORE();
     __syncthreads();
+    TC_BSTAMP(9);
     if ((tid & 31) == 0) {
       const uint32_t bytes = (uint32_t)(TC_BT * Hs * 4);
       for (int rr = warp; rr < C; rr += FWD_NT / 32) {
@@ -855,6 +898,12 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     for (int s = 0; s <= NSAVE; ++s)
 #pragma unroll
       for (int u = 0; u < NU; ++u) sv[s][u] = svn[s][u];
+    TC_BSTAMP(10);
+  }
+  if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) {
+    for (int i = 0; i < 12; ++i) a.dbg[64 + i] = bph[i];
+    a.dbg[76] = clock64() - bstart;
+    a.dbg[77] = t_end;
   }
 
   // ---- gradients of the learned initial states and of the peepholes
@@ -903,6 +952,7 @@ TcPlan tc_plan(int G, int H) {
     if (Hs * (C - 1) < H) { p.C = C; p.Hs = Hs; p.ok = true; break; }
   }
   if (!p.ok) return p;
+  constexpr int TC_BT = 16;   // sized for the larger tile; the 8-row tile needs half
   size_t f = (size_t)4 * p.Kp * TC_BT + (size_t)TC_BT * GSM_LD;
   p.smem = std::max<size_t>(f * sizeof(float), 120 * 1024);   // > half an SM: one CTA (one TMEM allocation) per SM
   // backward: MT tiles of 128 hidden rows, Kb = 4*Hs own gate columns, hi+lo: 32*MT + 2*MT*Kb TMEM columns
@@ -911,6 +961,33 @@ TcPlan tc_plan(int G, int H) {
   size_t fb = (size_t)2 * 4 * p.Hs * TC_BT + (size_t)4 * p.C * TC_BT * p.Hs;
   p.smem_bwd = std::max<size_t>(fb * sizeof(float), 120 * 1024);
   return p;
+}
+
+// Rows per cluster tile.  8-row tiles halve the per-step exchange and gate math but need twice the clusters: use
+// them when all the clusters of the batch are co-resident (B = 128 -> 16 clusters x 8 CTAs = 128 of the 148 SMs).
+// SBR_TC_BT=8|16 forces a choice (tests run both).
+template <typename Kern>
+int max_active_clusters(Kern kern, const TcPlan& p, size_t smem) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.C * 64, 1, 1);
+  cfg.blockDim = dim3(FWD_NT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int pick_rows_per_tile(const TcPlan& p, int B) {
+  if (const char* e = getenv("SBR_TC_BT")) { const int v = atoi(e); if (v == 8 || v == 16) return v; }
+  if (B % 8 != 0) return 16;
+  static int cached_C = -1, cached_n = 0;
+  if (cached_C != p.C) { cached_n = max_active_clusters(rnn_fwd_tc_kernel<4, 8>, p, p.smem); cached_C = p.C; }
+  return (B / 8 <= cached_n) ? 8 : 16;
 }
 
 template <typename Kern>
@@ -946,35 +1023,35 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   a.peep = m->params + L.peep; a.h_init = m->params + L.h_init; a.c_init = m->params + L.c_init;
   a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act; a.h_last = h_last;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
-  if (L.hT && B % TC_BT == 0) { a.hT = L.hT; a.hT_part = L.hT_part; a.hT_tile = L.hT_tile; }
-  const int n_tiles = cdiv(B, TC_BT);
+  const int BT = pick_rows_per_tile(p, B);
+  if (L.hT && B % BT == 0) { a.hT = L.hT; a.hT_part = L.hT_part; a.hT_tile = L.hT_tile; }
+  const int n_tiles = cdiv(B, BT);
   static long long* dbg = nullptr;
   if (getenv("SBR_TC_TIMELINE")) {
     if (!dbg) { cudaMalloc(&dbg, 80 * 8 * sizeof(long long)); cudaMemset(dbg, 0, 80 * 8 * sizeof(long long)); }
     a.dbg = dbg;
   }
-  if (L.G == 4) {
-    rc = launch_tc(m, rnn_fwd_tc_kernel<4>, p, n_tiles, a, FWD_NT);
-    if (rc == 0 && a.dbg) {
-      static int calls = 0;
-      if (++calls == 8) {
-        long long h[80 * 8];
-        cudaStreamSynchronize(m->stream);
-        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        double acc[12] = {0};
-        int n = (int)(h[517] > 0 ? h[517] : 1);
-        for (int i = 1; i < 12; ++i) acc[i] = (double)h[i];
-        fprintf(stderr, "[tc fwd tail] proxy_fence %.0f barrier %.0f bulk_issue %.0f stores+loop %.0f\n", acc[8] / n, acc[9] / n, acc[10] / n, acc[7] / n);
-        fprintf(stderr, "[tc fwd kernel, cycles] t_end %lld | entry->A_init_done %lld | ->loop_start %lld | loop %lld (%.0f/step) | ->exit %lld\n", h[517],
-                h[513] - h[512], h[514] - h[513], h[515] - h[514], (double)(h[515] - h[514]) / (double)(h[517] > 0 ? h[517] : 1), h[516] - h[515]);
-        fprintf(stderr, "[tc fwd timeline, cycles/step] total %.0f | wait_raw %.0f split+fence %.0f mma_issue %.0f mma_wait %.0f ldtm+bar %.0f gate+stas %.0f stg %.0f\n",
-                acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n, acc[7] / n);
-      }
+#define SBR_FWD_CASE(G_, BT_) if (L.G == G_ && BT == BT_) rc = launch_tc(m, rnn_fwd_tc_kernel<G_, BT_>, p, n_tiles, a, FWD_NT);
+  rc = 1;
+  SBR_FWD_CASE(4, 16) SBR_FWD_CASE(4, 8) SBR_FWD_CASE(3, 16) SBR_FWD_CASE(3, 8) SBR_FWD_CASE(1, 16) SBR_FWD_CASE(1, 8)
+#undef SBR_FWD_CASE
+  if (rc == 0 && a.dbg && L.G == 4) {
+    static int calls = 0;
+    if (++calls == 8) {
+      long long h[80 * 8];
+      cudaStreamSynchronize(m->stream);
+      cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      double acc[12] = {0};
+      int n = (int)(h[517] > 0 ? h[517] : 1);
+      for (int i = 1; i < 12; ++i) acc[i] = (double)h[i];
+      fprintf(stderr, "[tc fwd BT=%d tail] proxy_fence %.0f barrier %.0f bulk_issue %.0f stores+loop %.0f\n", BT, acc[8] / n, acc[9] / n, acc[10] / n, acc[7] / n);
+      fprintf(stderr, "[tc fwd kernel, cycles] t_end %lld | entry->A_init_done %lld | ->loop_start %lld | loop %lld (%.0f/step) | ->exit %lld\n", h[517],
+              h[513] - h[512], h[514] - h[513], h[515] - h[514], (double)(h[515] - h[514]) / (double)(h[517] > 0 ? h[517] : 1), h[516] - h[515]);
+      fprintf(stderr, "[tc fwd timeline, cycles/step] wait_peers %.0f arm %.0f mma_issue %.0f mma_wait %.0f ldtm+bar %.0f gate %.0f\n",
+              acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n);
     }
-    return rc;
   }
-  if (L.G == 3) return launch_tc(m, rnn_fwd_tc_kernel<3>, p, n_tiles, a, FWD_NT);
-  return launch_tc(m, rnn_fwd_tc_kernel<1>, p, n_tiles, a, FWD_NT);
+  return rc;
 }
 
 int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last) {
@@ -986,10 +1063,28 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.dh_last = dh_last; a.dhs = dh_last ? nullptr : L.dhs; a.dXg = L.dXg; a.dac = L.dac;
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
-  if (L.aT && B % TC_BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
+  const int BT = pick_rows_per_tile(p, B);
+  if (L.aT && B % BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
   a.g_b = m->grads + L.b;
-  const int n_tiles = cdiv(B, TC_BT);
-#define SBR_BWD_CASE(G_, MT_) if (L.G == G_ && p.MT == MT_) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_>, p, n_tiles, a, FWD_NT);
+  const int n_tiles = cdiv(B, BT);
+  if (getenv("SBR_TC_TIMELINE")) {
+    static long long* bdbg = nullptr;
+    static int calls = 0;
+    if (!bdbg) { cudaMalloc(&bdbg, 80 * 8 * sizeof(long long)); cudaMemset(bdbg, 0, 80 * 8 * sizeof(long long)); }
+    a.dbg = bdbg;
+    if (++calls == 9) {
+      long long h[80];
+      cudaStreamSynchronize(m->stream);
+      cudaMemcpy(h, bdbg + 64, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+      const double n = (double)(h[13] > 0 ? h[13] : 1);
+      fprintf(stderr, "[tc bwd BT=%d, cycles/step] total %.0f (t_end %lld) | issue_prefetch %.0f wait_parts+arm %.0f gate_grad %.0f fence %.0f barrier %.0f "
+              "dump+stores %.0f mma_wait %.0f ldtm+sbuf %.0f fence %.0f barrier %.0f bulk+copy %.0f\n", BT, h[12] / n, h[13],
+              0.0, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n);
+    }
+  }
+#define SBR_BWD_CASE(G_, MT_) \
+  if (L.G == G_ && p.MT == MT_ && BT == 16) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 16>, p, n_tiles, a, FWD_NT); \
+  if (L.G == G_ && p.MT == MT_ && BT == 8) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 8>, p, n_tiles, a, FWD_NT);
   SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)
 #undef SBR_BWD_CASE
   return 1;

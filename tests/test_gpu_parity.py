@@ -97,11 +97,22 @@ def test_cce_gradients(cell, H):
     check_grads(spec, B=11, T=9)
 
 
+@pytest.mark.parametrize("rows", ["8", "16"])
 @pytest.mark.parametrize("cell,H,B", [("LSTM", 200, 32), ("GRU", 100, 16), ("Vanilla", 48, 48), ("LSTM", 64, 128)])
-def test_cce_gradients_tensor_core_wgrad(cell, H, B):
-    """B % 16 == 0: the tcgen05 scans also emit the K-major hi/lo copies and dW_hid comes from wgrad_tc_kernel."""
+def test_cce_gradients_tensor_core_wgrad(cell, H, B, rows, monkeypatch):
+    """B % 16 == 0: the tcgen05 scans also emit the K-major hi/lo copies and dW_hid comes from wgrad_tc_kernel.
+    Both cluster-tile heights (8 and 16 batch rows, SBR_TC_BT) must give the same gradients."""
+    monkeypatch.setenv("SBR_TC_BT", rows)
     spec = O.Spec(n_items=211, cell=cell, layers=(H,), loss="CCE")
     check_grads(spec, B=B, T=11, seed=12)
+
+
+@pytest.mark.parametrize("cell,H", [("GRU", 100), ("LSTM", 200), ("Vanilla", 48), ("LSTM", 52)])
+def test_cce_gradients_8_row_tiles_ragged_batch(cell, H, monkeypatch):
+    """8-row cluster tiles with a batch that is not a multiple of 8 (last tile partly empty)."""
+    monkeypatch.setenv("SBR_TC_BT", "8")
+    spec = O.Spec(n_items=211, cell=cell, layers=(H,), loss="CCE", regularization=0.01)
+    check_grads(spec, B=11, T=9)
 
 
 @pytest.mark.parametrize("cell", ["GRU", "LSTM"])
