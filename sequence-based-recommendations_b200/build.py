@@ -1,6 +1,9 @@
 """Build libsbr_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python sequence-based-recommendations_b200/build.py [--force]
+    python sequence-based-recommendations_b200/build.py [--force] [-v] [--timeline]
+
+--timeline compiles the clock64 phase stamps into the tcgen05 scan kernels (profiling builds only; read them with
+SBR_TC_TIMELINE=1).
 """
 import os
 import subprocess
@@ -31,13 +34,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, timeline=False):
+    if not force and not timeline and not needs_build():
         return OUT
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if timeline:
+        flags.append("-DSBR_TC_TIMELINE_BUILD")
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
@@ -57,4 +62,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, timeline="--timeline" in sys.argv))

@@ -84,6 +84,7 @@ struct BatchSlot {       // device-resident inputs of one mini-batch
   int32_t* Y = nullptr;       // [n_all] targets (CCE: B)
   float* pop = nullptr;       // [B]
   int B = 0, t_max = 0, n_all = 0, row_offset = 0;
+  std::vector<int32_t> hlen;  // host copy of len (the scan launchers schedule their cluster tiles from it)
 };
 
 struct sbr_model {
@@ -144,6 +145,7 @@ struct sbr_model {
   int32_t* topk_ids = nullptr;
   // host staging (pinned)
   int32_t* h_len = nullptr;
+  const int32_t* cur_hlen = nullptr;  // host lengths of the batch being processed (BatchSlot::hlen), may be null
   float* h_cost = nullptr;
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;

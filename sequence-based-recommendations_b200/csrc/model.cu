@@ -245,8 +245,15 @@ static int create_impl(sbr_model* m) {
     return SBR_E_NOGPU;
   }
   m->n_sm = prop.multiProcessorCount;
-  CU_TRY(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  CU_TRY(m, cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+  {
+    // the critical path (scans) outranks the side stream: when both have CTAs pending, the 8-CTA clusters of a scan
+    // must not queue behind the output-layer weight-gradient GEMM
+    int lo = 0, hi = 0;
+    CU_TRY(m, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const bool prio = !getenv("SBR_NO_STREAM_PRIORITY");
+    CU_TRY(m, cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prio ? hi : 0));
+    CU_TRY(m, cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, prio ? lo : 0));
+  }
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   for (auto& e : m->ev) CU_TRY(m, cudaEventCreate(&e));
@@ -500,6 +507,7 @@ static int stage_common(sbr_model* m, BatchSlot& s, const int32_t* X, const floa
   if (rc) return rc;
   s.B = B;
   s.t_max = t_max;
+  s.hlen.assign(m->h_len, m->h_len + B);
   // pageable caller buffer -> pinned staging -> device (one DMA, no driver-side bounce)
   const size_t xbytes = (size_t)B * m->T * m->K * sizeof(int32_t);
   memcpy(m->h_stage, X, xbytes);
@@ -548,6 +556,7 @@ static int bias_rows(sbr_model* m, float* out, const float* bias, int64_t rows, 
 
 // ids -> final hidden state of the top layer (m->h_last)
 static int forward_stack(sbr_model* m, const BatchSlot& s) {
+  m->cur_hlen = (int)s.hlen.size() == s.B ? s.hlen.data() : nullptr;
   const int B = s.B, T = m->T, K = m->K, t_max = s.t_max;
   const int64_t rows = (int64_t)t_max * B;
   int rc;
@@ -584,6 +593,7 @@ static int side_return(sbr_model* m);
 
 // BPTT through the stack given m->dh_last; fills the gradient arena of every stack parameter
 static int backward_stack(sbr_model* m, const BatchSlot& s) {
+  m->cur_hlen = (int)s.hlen.size() == s.B ? s.hlen.data() : nullptr;
   const int B = s.B, T = m->T, K = m->K, t_max = s.t_max;
   const int rows = t_max * B;
   int rc;
@@ -635,12 +645,14 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
 // while the BPTT scan runs on 64 of the 148 SMs; the scatter while the weight-gradient GEMM runs) is
 // launched on m->side between side_fork() and side_join(); the two streams write disjoint gradient blocks.
 static int side_fork(sbr_model* m) {
+  if (getenv("SBR_NO_SIDE_STREAM")) return 0;   // diagnostics: everything on one stream
   CU_TRY(m, cudaEventRecord(m->ev_fork, m->stream));
   CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
   std::swap(m->stream, m->side);     // launchers use m->stream
   return 0;
 }
 static int side_return(sbr_model* m) {   // back to the main stream; the side work keeps running
+  if (getenv("SBR_NO_SIDE_STREAM")) return 0;
   std::swap(m->stream, m->side);
   return 0;
 }

@@ -24,6 +24,7 @@
 // Applicability: H % 4 == 0, H <= 240 (hi+lo copies of the K extent must fit in 512 TMEM columns),
 // otherwise launch_rnn_* falls back to the FFMA cluster kernels.
 #include <cooperative_groups.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -46,6 +47,8 @@ struct TcArgs {
   float* hT; float* aT;                 // K-major pre-split copies for the tensor-core wgrad GEMM (may be null)
   float* g_b;                           // bias gradient slot (backward accumulates sum dXg itself when set)
   long long hT_part, hT_tile, aT_part, aT_tile;
+  int use_order;                        // cluster c works on tile order[c] (longest tiles first) instead of tile c
+  unsigned char order[64];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
-  const int tile = blockIdx.x / C;
+  const int tile = a.use_order ? (int)a.order[blockIdx.x / C] : (int)(blockIdx.x / C);
   const int b0 = tile * TC_BT;
   const int H = a.H, Hs = a.Hs, Kp = a.Kp, GH = G * H, B = a.B;
   const int KS = Kp / 8;
@@ -227,7 +230,11 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   __shared__ int lens_s[TC_BT];
   __shared__ int t_end_s;
 
+#ifdef SBR_TC_TIMELINE_BUILD   // in-kernel clock64 timeline: compiled in only for profiling builds (build.py --timeline)
 #define TC_KSTAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) a.dbg[512 + (i)] = clock64(); } while (0)
+#else
+#define TC_KSTAMP(i) do { } while (0)
+#endif
   TC_KSTAMP(0);
   if (tid < TC_BT) lens_s[tid] = (b0 + tid < B) ? min(a.len[b0 + tid], a.t_max) : 0;
   if (tid == 0) {
@@ -359,9 +366,13 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   const int hoff = ((j0 + ju) >> 2) * KCB + eb * 4 + (ju & 3);   // float offset of this thread's units in a buffer
 
   TC_KSTAMP(2);
+#ifdef SBR_TC_TIMELINE_BUILD
   if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) a.dbg[512 + 5] = t_end;
   long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last_stamp = 0;
 #define TC_STAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) { const long long now_ = clock64(); if ((i) > 0) ph[i] += now_ - last_stamp; last_stamp = now_; } } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#endif
   for (int t = 0; t < t_end; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
     TC_STAMP(0);
@@ -495,7 +506,9 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   }
 
   TC_KSTAMP(3);
+#ifdef SBR_TC_TIMELINE_BUILD
   if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) for (int i = 0; i < 12; ++i) a.dbg[i] = ph[i];
+#endif
   // final state: wait for the last exchange (only the own slice is written out)
   if (t_end > 0) {
     const int fin = t_end & 1;
@@ -531,7 +544,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
-  const int tile = blockIdx.x / C;
+  const int tile = a.use_order ? (int)a.order[blockIdx.x / C] : (int)(blockIdx.x / C);
   const int b0 = tile * TC_BT;
   const int H = a.H, Hs = a.Hs, GH = G * H, B = a.B;
   const int Kb = 4 * Hs;                 // contraction length: own gate columns, kk = 4*j + g
@@ -724,9 +737,13 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   const uint32_t bar_addr[2] = {smem_u32(&part_full[0]), smem_u32(&part_full[1])};
   int n_wait[2] = {0, 0};      // completed phases of each part_full barrier
 
+#ifdef SBR_TC_TIMELINE_BUILD
   long long bph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, blast = 0;
 #define TC_BSTAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) { const long long now_ = clock64(); if ((i) > 0) bph[i] += now_ - blast; blast = now_; } } while (0)
   const long long bstart = a.dbg ? clock64() : 0;
+#else
+#define TC_BSTAMP(i) do { } while (0)
+#endif
   for (int t = t_end - 1; t >= 0; --t) {
     const int par = t & 1, rpar = par ^ 1;
     TC_BSTAMP(0);
@@ -900,11 +917,13 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
       for (int u = 0; u < NU; ++u) sv[s][u] = svn[s][u];
     TC_BSTAMP(10);
   }
+#ifdef SBR_TC_TIMELINE_BUILD
   if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) {
     for (int i = 0; i < 12; ++i) a.dbg[64 + i] = bph[i];
     a.dbg[76] = clock64() - bstart;
     a.dbg[77] = t_end;
   }
+#endif
 
   // ---- gradients of the learned initial states and of the peepholes
   if (t_end > 0) {
@@ -982,12 +1001,65 @@ int max_active_clusters(Kern kern, const TcPlan& p, size_t smem) {
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
-int pick_rows_per_tile(const TcPlan& p, int B) {
-  if (const char* e = getenv("SBR_TC_BT")) { const int v = atoi(e); if (v == 8 || v == 16) return v; }
-  if (B % 8 != 0) return 16;
+int resident_clusters(const TcPlan& p) {
   static int cached_C = -1, cached_n = 0;
-  if (cached_C != p.C) { cached_n = max_active_clusters(rnn_fwd_tc_kernel<4, 8>, p, p.smem); cached_C = p.C; }
-  return (B / 8 <= cached_n) ? 8 : 16;
+  if (cached_C != p.C) {
+    cached_n = max_active_clusters(rnn_fwd_tc_kernel<4, 8>, p, p.smem);
+    cached_C = p.C;
+    if (getenv("SBR_TC_VERBOSE")) fprintf(stderr, "[tc] clusters of %d CTAs co-resident: %d\n", p.C, cached_n);
+  }
+  return cached_n;
+}
+// Tile schedule of one scan launch.  The hardware hands clusters to free SM groups in blockIdx order, i.e. list
+// scheduling on `slots` machines (15 eight-CTA clusters fit on a B200: seven GPCs take two, one takes one).  With
+// the host copy of the lengths the launcher (a) sorts the tiles longest first, so that when there are more tiles
+// than slots the short ones queue behind clusters that finish early, and (b) takes 8-row tiles only when their
+// makespan (x the measured per-step cost ratio of an 8-row vs a 16-row tile) beats the 16-row tiling.
+struct TileSched { int BT; int n_tiles; int use_order; unsigned char order[64]; };
+int makespan(const int* t_end, int n, int slots) {   // t_end sorted descending
+  std::vector<int> busy(std::max(1, slots), 0);
+  for (int i = 0; i < n; ++i) {
+    auto it = std::min_element(busy.begin(), busy.end());
+    *it += t_end[i];
+  }
+  return *std::max_element(busy.begin(), busy.end());
+}
+TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, float ratio8) {
+  TileSched sc{};
+  const int slots = resident_clusters(p);
+  const int32_t* hl = m->cur_hlen;
+  auto tiles_of = [&](int BT, int* t_end, unsigned char* order) {
+    const int n = cdiv(B, BT);
+    std::vector<std::pair<int, int>> v(n);
+    for (int i = 0; i < n; ++i) {
+      int mx = 0;
+      for (int b = i * BT; b < std::min(B, (i + 1) * BT); ++b) mx = std::max(mx, std::min(hl[b], t_max));
+      v[i] = {-mx, i};
+    }
+    std::sort(v.begin(), v.end());
+    for (int i = 0; i < n; ++i) { t_end[i] = -v[i].first; order[i] = (unsigned char)v[i].second; }
+    return n;
+  };
+  int forced = 0;
+  if (const char* e = getenv("SBR_TC_BT")) { const int v = atoi(e); if (v == 8 || v == 16) forced = v; }
+  if (!hl || cdiv(B, 8) > 64) {           // no host lengths (or too many tiles to reorder): static rule
+    sc.BT = forced ? forced : ((B % 8 == 0 && B / 8 <= slots) ? 8 : 16);
+    sc.n_tiles = cdiv(B, sc.BT);
+    return sc;
+  }
+  int t8[64], t16[64];
+  unsigned char o8[64], o16[64];
+  const int n8 = tiles_of(8, t8, o8), n16 = tiles_of(16, t16, o16);
+  int BT = forced;
+  if (!BT) {
+    const float c8 = ratio8 * (float)makespan(t8, n8, slots), c16 = (float)makespan(t16, n16, slots);
+    BT = (B % 8 == 0 && c8 < c16) ? 8 : 16;
+  }
+  sc.BT = BT;
+  sc.n_tiles = BT == 8 ? n8 : n16;
+  sc.use_order = 1;
+  memcpy(sc.order, BT == 8 ? o8 : o16, 64);
+  return sc;
 }
 
 template <typename Kern>
@@ -1023,9 +1095,11 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   a.peep = m->params + L.peep; a.h_init = m->params + L.h_init; a.c_init = m->params + L.c_init;
   a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act; a.h_last = h_last;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
-  const int BT = pick_rows_per_tile(p, B);
+  const TileSched sc = schedule_tiles(m, p, B, t_max, 0.71f);   // fwd: 2914 vs 4114 cycles per step (8 vs 16 rows)
+  const int BT = sc.BT, n_tiles = sc.n_tiles;
+  a.use_order = sc.use_order;
+  memcpy(a.order, sc.order, sizeof(a.order));
   if (L.hT && B % BT == 0) { a.hT = L.hT; a.hT_part = L.hT_part; a.hT_tile = L.hT_tile; }
-  const int n_tiles = cdiv(B, BT);
   static long long* dbg = nullptr;
   if (getenv("SBR_TC_TIMELINE")) {
     if (!dbg) { cudaMalloc(&dbg, 80 * 8 * sizeof(long long)); cudaMemset(dbg, 0, 80 * 8 * sizeof(long long)); }
@@ -1063,10 +1137,12 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.dh_last = dh_last; a.dhs = dh_last ? nullptr : L.dhs; a.dXg = L.dXg; a.dac = L.dac;
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
-  const int BT = pick_rows_per_tile(p, B);
+  const TileSched sc = schedule_tiles(m, p, B, t_max, 0.75f);   // bwd: 4118 vs 5477 cycles per step (8 vs 16 rows)
+  const int BT = sc.BT, n_tiles = sc.n_tiles;
+  a.use_order = sc.use_order;
+  memcpy(a.order, sc.order, sizeof(a.order));
   if (L.aT && B % BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
   a.g_b = m->grads + L.b;
-  const int n_tiles = cdiv(B, BT);
   if (getenv("SBR_TC_TIMELINE")) {
     static long long* bdbg = nullptr;
     static int calls = 0;
