@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsbr_b200.so")
+# SBR_B200_LIB selects another build of the same library (e.g. the --timeline profiling build)
+LIB_PATH = os.environ.get("SBR_B200_LIB") or os.path.join(_HERE, "libsbr_b200.so")
 
 SBR_MAX_LAYERS = 8
 SBR_NCCL_ID_BYTES = 128

@@ -44,7 +44,7 @@ def build(force=False, verbose=False, timeline=False):
     if timeline:
         flags.append("-DSBR_TC_TIMELINE_BUILD")
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "build", src.replace(".cu", "_tl.o" if timeline else ".o"))
         objs.append(obj)
         cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -56,9 +56,10 @@ def build(force=False, verbose=False, timeline=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [_nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    out = OUT.replace(".so", "_timeline.so") if timeline else OUT
+    link = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(link)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

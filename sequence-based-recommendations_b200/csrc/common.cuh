@@ -95,6 +95,7 @@ struct sbr_model {
   cudaStream_t side = nullptr;        // off-critical-path work (see side_fork / side_join in model.cu)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool side_pending = false;
+  int deferred_out_B = 0;             // >0: output-layer weight gradients still to be launched on the side stream
   bool staging_in_flight = false;     // pinned staging buffers still feed an H2D copy
   std::string err;
   int err_code = 0;

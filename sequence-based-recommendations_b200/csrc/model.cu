@@ -590,6 +590,7 @@ static int forward_stack(sbr_model* m, const BatchSlot& s) {
 
 static int side_fork(sbr_model* m);
 static int side_return(sbr_model* m);
+static int launch_deferred_output_grads(sbr_model* m);
 
 // BPTT through the stack given m->dh_last; fills the gradient arena of every stack parameter
 static int backward_stack(sbr_model* m, const BatchSlot& s) {
@@ -601,6 +602,8 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
     LayerDesc& L = m->layers[li];
     const int H = L.H, GH = L.G * L.H;
     if ((rc = launch_rnn_backward(m, L, s.len, B, t_max, li == m->L - 1 ? m->dh_last : nullptr))) return rc;
+    // the scan is in the launch queue first, so its clusters get their SMs before the side-stream GEMM's CTAs do
+    if (li == m->L - 1 && (rc = launch_deferred_output_grads(m))) return rc;
     if (li == 0) stage_mark(m, 5);
     const bool gather_layer = (li == 0 && m->E == 0);
     if (gather_layer) {
@@ -668,12 +671,31 @@ static int output_backward_full(sbr_model* m, int B) {
   int rc;
   // critical path: dh_last feeds the BPTT scan
   if ((rc = launch_gemm(m, false, false, B, H, N, m->logits, N, m->params + m->out_WT, H, m->dh_last, H, 1.f, 0.f))) return rc;
-  // off the critical path: dW_out^T and db_out on the side stream, joined before the all-reduce
-  if ((rc = side_fork(m))) return rc;
-  rc = launch_gemm(m, true, false, N, H, B, m->logits, N, m->h_last, H, m->grads + m->out_WT, H, 1.f, 1.f);
+  // off the critical path: dW_out^T and db_out go to the side stream (joined before the all-reduce).  The fork point
+  // is here (they only need the logit gradients and h_last), but the launches are issued AFTER the BPTT scan has
+  // been launched on the main stream (launch_deferred_output_grads): a GEMM that reaches the SMs first would keep
+  // some of the scan's 8-CTA clusters waiting for free SMs.
+  if (!getenv("SBR_NO_SIDE_STREAM")) CU_TRY(m, cudaEventRecord(m->ev_fork, m->stream));
+  m->deferred_out_B = B;
+  return 0;
+}
+
+static int launch_deferred_output_grads(sbr_model* m) {
+  const int B = m->deferred_out_B;
+  if (B <= 0) return 0;
+  m->deferred_out_B = 0;
+  const int N = m->N, H = m->H_last;
+  const bool side = !getenv("SBR_NO_SIDE_STREAM");
+  if (side) {
+    CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+    std::swap(m->stream, m->side);
+  }
+  int rc = launch_gemm(m, true, false, N, H, B, m->logits, N, m->h_last, H, m->grads + m->out_WT, H, 1.f, 1.f);
   if (!rc) rc = launch_colsum(m, m->logits, B, N, N, m->grads + m->out_b);
-  side_return(m);
-  m->side_pending = true;
+  if (side) {
+    std::swap(m->stream, m->side);
+    m->side_pending = true;
+  }
   return rc;
 }
 

@@ -47,6 +47,8 @@ struct TcArgs {
   float* hT; float* aT;                 // K-major pre-split copies for the tensor-core wgrad GEMM (may be null)
   float* g_b;                           // bias gradient slot (backward accumulates sum dXg itself when set)
   long long hT_part, hT_tile, aT_part, aT_tile;
+  int ld_p;                             // backward loader: steps of saved activations in flight
+  int xflags;                           // SBR_TC_EXPERIMENT bit mask (timing experiments only: results are wrong)
   int use_order;                        // cluster c works on tile order[c] (longest tiles first) instead of tile c
   unsigned char order[64];
 };
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   __shared__ int t_end_s;
 
 #ifdef SBR_TC_TIMELINE_BUILD   // in-kernel clock64 timeline: compiled in only for profiling builds (build.py --timeline)
-#define TC_KSTAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) a.dbg[512 + (i)] = clock64(); } while (0)
+#define TC_KSTAMP(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[512 + (i)] = clock64(); } while (0)
 #else
 #define TC_KSTAMP(i) do { } while (0)
 #endif
@@ -298,8 +300,11 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 
   TC_KSTAMP(1);
   // ---- gate-math ownership: row eb, units ju .. ju+NU-1 of the slice
-  const int eb = tid / TPR;
-  const int ju = NU * (tid % TPR);
+  // 16-row tiles: a warp = 2 rows x 16 unit pairs (global accesses of a row are contiguous).  8-row tiles: a warp =
+  // all 8 rows x 4 consecutive units, so that its writes into the B operand ([unit/4][row][4]) cover 32 consecutive
+  // words instead of hitting one bank group 8 times.
+  const int eb = (BT == 8) ? (tid & 7) : tid / TPR;
+  const int ju = (BT == 8) ? (warp * 4 + ((tid & 31) >> 3)) : NU * (tid % TPR);
   const bool own = ju < nj;                       // nj is a multiple of 4 (H % 4 == 0, Hs % 4 == 0)
   const bool row_ok = b0 + eb < B;
   float cst[NU], wci[NU], wcf[NU], wco[NU];
@@ -367,9 +372,9 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 
   TC_KSTAMP(2);
 #ifdef SBR_TC_TIMELINE_BUILD
-  if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) a.dbg[512 + 5] = t_end;
+  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[512 + 5] = t_end;
   long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last_stamp = 0;
-#define TC_STAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) { const long long now_ = clock64(); if ((i) > 0) ph[i] += now_ - last_stamp; last_stamp = now_; } } while (0)
+#define TC_STAMP(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); if ((i) > 0) ph[i] += now_ - last_stamp; last_stamp = now_; } } while (0)
 #else
 #define TC_STAMP(i) do { } while (0)
 #endif
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     }
     TC_STAMP(3);
     // input pre-activations of the NEXT step: in flight while the tensor core works
-    if (t + 1 < t_end) load_x(t + 1, xn);
+    if (t + 1 < t_end && !(a.xflags & 16)) load_x(t + 1, xn);
     mbar_wait_cta(&mma_done, t & 1);
     TC_STAMP(4);
     TC_FENCE_AFTER();
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     }
     TC_STAMP(10);
     // saved trajectories for the backward pass: issued last so that nothing on the critical path waits on them
-    if (own && row_ok) {
+    if (own && row_ok && !(a.xflags & 32)) {
       const int64_t row1 = (int64_t)(t + 1) * B + b0 + eb;
       stn<NU>(a.hs + row1 * H + j0 + ju, hn);
       if (G == 4) stn<NU>(a.cs + row1 * H + j0 + ju, cst);
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
         }
       }
     }
-    dump_hT(hbuf + nxt * HB, t + 1);
+    if (!(a.xflags & 64)) dump_hT(hbuf + nxt * HB, t + 1);
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 
   TC_KSTAMP(3);
 #ifdef SBR_TC_TIMELINE_BUILD
-  if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) for (int i = 0; i < 12; ++i) a.dbg[i] = ph[i];
+  if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 12; ++i) a.dbg[i] = ph[i];
 #endif
   // final state: wait for the last exchange (only the own slice is written out)
   if (t_end > 0) {
@@ -535,12 +540,22 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 // ------------------------------------------------------------------------------------------------
 // TMEM map (MT = number of 128-row tiles of the hidden index k, Kb = 4*Hs own gate columns):
 //   D1_mt at 32*mt, D2_mt at 32*mt+16; A_mt_hi at 32*MT + mt*2*Kb, A_mt_lo right after it.
+// Threads: 8 compute warps (as in the forward kernel) + BT/8 LOADER warps.  The saved activations of a step (gates,
+// cell states, gradient from the layer above) come from global memory; when the compute threads fetched them
+// themselves, the fence.proxy.async they must execute before every MMA / bulk copy (a MEMBAR that drains the thread's
+// outstanding loads) put the full L2/HBM latency of that prefetch on the per-step critical path (measured: 0.33 ->
+// 0.22 ms for the whole scan without the loads).  The loader warps never fence: they issue the 16-byte loads of step
+// t-3 while step t runs, park them in registers for one step, and drop them into a double-buffered shared staging
+// area that the compute threads read with plain LDS.
+constexpr int bwd_threads(int BT) { return FWD_NT + 32 * (BT / 8); }
+
 template <int G, int MT, int BT>
-__global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const TcArgs a) {
   constexpr int TC_BT = BT;
   constexpr int TPR = FWD_NT / BT;
   constexpr int NU = 32 / TPR;
   constexpr int QB = BT / 4;
+  constexpr int NLT = 32 * (BT / 8);     // loader threads
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
@@ -562,6 +577,9 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
   float* part = Blo + Kb * TC_BT;               // [2][C][16][Hs] partial dh received from the peers (bulk copies)
   float* sbuf = part + 2 * C * TC_BT * Hs;      // [2][C][16][Hs] partial dh of this CTA, grouped by owner (send buffer)
   const int PB = C * TC_BT * Hs;                // floats per part / send buffer
+  float* stag = sbuf + 2 * PB;                  // [4][7][BT][Hs] saved tensors of a step, filled by the loader warps
+  const int SGB = 7 * TC_BT * Hs;
+  const bool ldr = tid >= FWD_NT;               // loader warp(s): no MMA, no gate math, no fences
   __shared__ __align__(8) uint64_t part_full[2];
   __shared__ __align__(8) uint64_t mma_done;
   __shared__ uint32_t tmem_base_s;
@@ -579,8 +597,10 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < 2 * Kb * TC_BT; i += FWD_NT) Bhi[i] = 0.f;            // Bhi and Blo are contiguous
-  for (int i = tid; i < 4 * C * TC_BT * Hs; i += FWD_NT) part[i] = 0.f;          // part and sbuf are contiguous
+  if (!ldr) {
+    for (int i = tid; i < 2 * Kb * TC_BT; i += FWD_NT) Bhi[i] = 0.f;            // Bhi and Blo are contiguous
+    for (int i = tid; i < 4 * C * TC_BT * Hs; i += FWD_NT) part[i] = 0.f;          // part and sbuf are contiguous
+  }
   TC_FENCE_BEFORE();
   __syncthreads();
   TC_FENCE_AFTER();
@@ -593,7 +613,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
 
   // ---- A operand tiles: row = hidden index k, column kk = 4*j + g  <->  W_hid[k][g*H + j0 + j]
   //      warps 0-3 stage the hi copies, warps 4-7 the lo copies
-  {
+  if (!ldr) {
     const bool want_lo = warp >= 4;
     for (int mt = 0; mt < MT; ++mt) {
       const int k = mt * 128 + quad * 32 + (tid & 31);
@@ -625,9 +645,11 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 
-  const int eb = tid / TPR;
-  const int ju = NU * (tid % TPR);
-  const bool own = ju < nj;
+  // thread <-> (row, unit) as in the forward kernel: with 8-row tiles a warp's 16-byte stores of da into the B
+  // operand ([unit][row][4 gates]) are 512 contiguous bytes (conflict-free) instead of 32 hits on one bank group
+  const int eb = ldr ? 0 : ((BT == 8) ? (tid & 7) : tid / TPR);
+  const int ju = (BT == 8) ? (warp * 4 + ((tid & 31) >> 3)) : NU * (tid % TPR);
+  const bool own = !ldr && ju < nj;
   const bool row_ok = b0 + eb < B;
   float carry[NU], dcs[NU], dpe[NU][3], wci[NU], wcf[NU], wco[NU];
   float dbias[NU][4];                                                   // sum over steps of dXg (bias gradient)
@@ -694,37 +716,96 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     }
   }
 
-  // saved tensors of a step for this thread's 4 units: [slot][unit]
+  // saved tensors of a step for this thread's units: [slot][unit]
   //  LSTM: i f g o c_prev c_new | GRU: r u cand a_c h_prev | Vanilla: h_new ; last slot: dhs from above
   constexpr int NSAVE = (G == 4) ? 6 : (G == 3 ? 5 : 1);
-  float sv[NSAVE + 1][NU], svn[NSAVE + 1][NU];
+  const int NA = NSAVE + (a.dhs ? 1 : 0);          // arrays staged per step
+  float sv[NSAVE + 1][NU];
 #pragma unroll
   for (int s = 0; s <= NSAVE; ++s)
 #pragma unroll
-    for (int u = 0; u < NU; ++u) sv[s][u] = svn[s][u] = 0.f;
-  auto ld4f = [](const float* p, float (&d)[NU]) { ldgn<NU>(p, d); };
-  auto load_saved = [&](int t, float (&s)[NSAVE + 1][NU]) {
-    if (own && t < lens_s[eb]) {
-      const int64_t row = (int64_t)t * B + b0 + eb;
-      if constexpr (G == 4) {
-        const float* ap = a.act + row * 4 * H + j0 + ju;
-        ld4f(ap, s[0]); ld4f(ap + H, s[1]); ld4f(ap + 2 * H, s[2]); ld4f(ap + 3 * H, s[3]);
-        ld4f(a.cs + row * H + j0 + ju, s[4]);
-        ld4f(a.cs + (row + B) * H + j0 + ju, s[5]);
-      } else if constexpr (G == 3) {
-        const float* ap = a.act + row * 4 * H + j0 + ju;
-        ld4f(ap, s[0]); ld4f(ap + H, s[1]); ld4f(ap + 2 * H, s[2]); ld4f(ap + 3 * H, s[3]);
-        ld4f(a.hs + row * H + j0 + ju, s[4]);
-      } else {
-        ld4f(a.hs + (row + B) * H + j0 + ju, s[0]);
-      }
-      if (a.dhs) ld4f(a.dhs + row * H + j0 + ju, s[NSAVE]);
+    for (int u = 0; u < NU; ++u) sv[s][u] = 0.f;
+
+  // ---- loader: lane <-> up to two (row, unit quad) pairs of the CTA's [BT x Hs] slice; one 16-byte cp.async per
+  //      array straight into the staging ring (LD_D stages, LD_P steps ahead: the activations come back from HBM
+  //      with ~2 us latency under load, i.e. more than one step)
+  constexpr int LNP = 2;                           // BT * (Hs/4) <= BT * 8 pairs over 32 * BT/8 loader threads
+  constexpr int LD_D = 4;
+  const int LD_P = a.ld_p;                          // 1 .. LD_D - 1 steps ahead
+  auto ldr_wait = [&]() {                           // all but the LD_P - 1 most recent groups have landed
+    switch (LD_P) {
+      case 1: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+      case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+      case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+      case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      case 5: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+      case 6: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+      default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
     }
   };
-  if (t_end > 0) load_saved(t_end - 1, sv);
+  int l_b[LNP], l_soff[LNP];
+  long long l_g4[LNP], l_g1[LNP];                  // element offsets into [rows x 4H] / [rows x H] arrays
+  bool l_ok[LNP];
+  if (ldr) {
+    const int HQ = Hs >> 2;
+#pragma unroll
+    for (int pp = 0; pp < LNP; ++pp) {
+      const int pair = (tid - FWD_NT) + pp * NLT;
+      const int b = pair / HQ, q = pair - b * HQ;
+      l_ok[pp] = b < TC_BT && 4 * q < nj && b0 + b < B;
+      l_b[pp] = l_ok[pp] ? b : 0;
+      l_soff[pp] = b * Hs + 4 * q;
+      l_g4[pp] = (long long)(b0 + b) * 4 * H + j0 + 4 * q;
+      l_g1[pp] = (long long)(b0 + b) * H + j0 + 4 * q;
+    }
+  }
+  auto cp16 = [](float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+  };
+  auto ldr_issue = [&](int t) {      // one commit group per step, empty when t < 0
+    if (t >= 0 && !(a.xflags & 128)) {
+      float* sg = stag + (t & (LD_D - 1)) * SGB;
+#pragma unroll
+      for (int pp = 0; pp < LNP; ++pp) {
+        if (!(l_ok[pp] && t < lens_s[l_b[pp]])) continue;
+        const long long r4 = (long long)t * B * 4 * H + l_g4[pp], r1 = (long long)t * B * H + l_g1[pp];
+        float* d = sg + l_soff[pp];
+        const int AS = TC_BT * Hs;
+        if constexpr (G == 4) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) cp16(d + g * AS, a.act + r4 + g * H);
+          cp16(d + 4 * AS, a.cs + r1);
+          cp16(d + 5 * AS, a.cs + r1 + (long long)B * H);
+        } else if constexpr (G == 3) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) cp16(d + g * AS, a.act + r4 + g * H);
+          cp16(d + 4 * AS, a.hs + r1);
+        } else {
+          cp16(d, a.hs + r1 + (long long)B * H);
+        }
+        if (a.dhs) cp16(d + NSAVE * AS, a.dhs + r1);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // compute threads: this step's saved tensors out of the staging buffer (rows past their length are never used)
+  auto fetch_saved = [&](int t) {
+    if (own && t < lens_s[eb]) {
+      const float* sg = stag + (t & (LD_D - 1)) * SGB + eb * Hs + ju;
+#pragma unroll
+      for (int s2 = 0; s2 < NSAVE + 1; ++s2)
+        if (s2 < NA) ldn<NU>(sg + s2 * TC_BT * Hs, sv[s2]);
+    }
+  };
+  if (ldr) {
+    // LD_P steps in flight; the first one must have landed before the loop starts (the cluster barrier below
+    // publishes it to the compute threads)
+    for (int i = 1; i <= LD_P; ++i) ldr_issue(t_end - i);
+    ldr_wait();
+  }
 
   // one phase of part_full[x] = the partial dh blocks of my units have landed from the C-1 other CTAs
-  const uint32_t tx_bytes = (uint32_t)((C - 1) * TC_BT * Hs * 4);
+  const uint32_t tx_bytes = (a.xflags & 8) ? (uint32_t)((C - 1) * 16) : (uint32_t)((C - 1) * TC_BT * Hs * 4);
   if (tid == 0) {
     mbar_arrive_expect_tx(&part_full[0], tx_bytes);
     mbar_arrive_expect_tx(&part_full[1], tx_bytes);
@@ -739,18 +820,50 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
 
 #ifdef SBR_TC_TIMELINE_BUILD
   long long bph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, blast = 0;
-#define TC_BSTAMP(i) do { if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) { const long long now_ = clock64(); if ((i) > 0) bph[i] += now_ - blast; blast = now_; } } while (0)
+#define TC_BSTAMP(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); if ((i) > 0) bph[i] += now_ - blast; blast = now_; } } while (0)
   const long long bstart = a.dbg ? clock64() : 0;
 #else
 #define TC_BSTAMP(i) do { } while (0)
 #endif
+  // TMEM lane of this thread = hidden index k of tile warp/4; its owner CTA and slot there (loop-invariant)
+  const int k_mine = (warp >> 2) * 128 + quad * 32 + (tid & 31);
+  const int sb_off = (k_mine < H && (warp >> 2) < MT) ? ((k_mine / Hs) * TC_BT) * Hs + (k_mine % Hs) : -1;
   for (int t = t_end - 1; t >= 0; --t) {
     const int par = t & 1, rpar = par ^ 1;
     TC_BSTAMP(0);
-    if (t > 0) load_saved(t - 1, svn);
+    if (!(a.xflags & 4)) fetch_saved(t);
+
+    // ---- everything of the gate gradients that does not depend on dh_t is computed BEFORE waiting for the
+    //      partial sums of step t+1 (the exchange is in flight meanwhile): after the wait only a short chain of
+    //      multiplies by these coefficients remains on the critical path
+    const bool active = own && t < lens_s[eb];
+    float kc[NU][5];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      kc[u][0] = kc[u][1] = kc[u][2] = kc[u][3] = kc[u][4] = 0.f;
+      if (active) {
+        if constexpr (G == 4) {
+          const float ig = sv[0][u], fg = sv[1][u], gg = sv[2][u], og = sv[3][u], c_prev = sv[4][u];
+          const float tc = tanhf_(sv[5][u]);
+          kc[u][0] = tc * og * (1.f - og);          // do_pre = d * kc0
+          kc[u][1] = og * (1.f - tc * tc);          // dct    = dcs + d * kc1 + do_pre * wco
+          kc[u][2] = gg * ig * (1.f - ig);          // di_pre = dct * kc2
+          kc[u][3] = c_prev * fg * (1.f - fg);      // df_pre = dct * kc3
+          kc[u][4] = ig * (1.f - gg * gg);          // dg_pre = dct * kc4
+        } else if constexpr (G == 3) {
+          const float r = sv[0][u], uu = sv[1][u], cand = sv[2][u], ac = sv[3][u], h_prev = sv[4][u];
+          kc[u][0] = (cand - h_prev) * uu * (1.f - uu);   // du_pre = d * kc0
+          kc[u][1] = uu * (1.f - cand * cand);            // dq     = clip(d * kc1)
+          kc[u][2] = ac * r * (1.f - r);                  // dr_pre = dq * kc2
+          kc[u][3] = 1.f - uu;                            // carry  = d * kc3
+        } else {
+          kc[u][0] = 1.f - sv[0][u] * sv[0][u];           // dq = clip(d * kc0)
+        }
+      }
+    }
 
     // ---- phase A: dh_t = carry + partials of step t+1 (+ gradient from the layer above); gate gradients
-    if (t < t_end - 1) {
+    if (t < t_end - 1 && !ldr) {
       mbar_wait_cluster(&part_full[rpar], n_wait[rpar] & 1);
       n_wait[rpar]++;
       if (tid == 0) mbar_arrive_expect_tx(&part_full[rpar], tx_bytes);
@@ -762,17 +875,22 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
 #pragma unroll
       for (int u = 0; u < NU; ++u) dh[u] = carry[u];
       if (t < t_end - 1) {
-        for (int src = 0; src < C; ++src) {
-          // own contribution straight from the send buffer of step t+1, the others from the received blocks
-          const float* base = (src == rank) ? sbuf + rpar * PB : part + rpar * PB;
-          float p[NU];
-          ldn<NU>(base + (src * TC_BT + eb) * Hs + ju, p);
+        // own contribution straight from the send buffer of step t+1, the others from the received blocks;
+        // all loads first (independent), then the adds
+        float p[8][NU];
 #pragma unroll
-          for (int u = 0; u < NU; ++u) dh[u] += p[u];
+        for (int src = 0; src < 8; ++src) {
+#pragma unroll
+          for (int u = 0; u < NU; ++u) p[src][u] = 0.f;
+          if (src < C) {
+            const float* base = (src == rank) ? sbuf + rpar * PB : part + rpar * PB;
+            ldn<NU>(base + (src * TC_BT + eb) * Hs + ju, p[src]);
+          }
         }
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+          dh[u] += ((p[0][u] + p[1][u]) + (p[2][u] + p[3][u])) + ((p[4][u] + p[5][u]) + (p[6][u] + p[7][u]));
       }
-      const bool active = t < lens_s[eb];
-      const int64_t row = (int64_t)t * B + b0 + eb;
       float da[NU][4], dx[NU][4];   // [unit][gate]
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
@@ -782,14 +900,12 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
         if (active) {
           const float d = dh[u] + sv[NSAVE][u];
           if constexpr (G == 4) {
-            const float ig = sv[0][u], fg = sv[1][u], gg = sv[2][u], og = sv[3][u];
-            const float c_prev = sv[4][u], c_new = sv[5][u];
-            const float tc = tanhf_(c_new);
-            const float do_pre = d * tc * og * (1.f - og);
-            const float dct = dcs[u] + d * og * (1.f - tc * tc) + do_pre * wco[u];
-            const float di_pre = dct * gg * ig * (1.f - ig);
-            const float df_pre = dct * c_prev * fg * (1.f - fg);
-            const float dg_pre = dct * ig * (1.f - gg * gg);
+            const float fg = sv[1][u], c_prev = sv[4][u], c_new = sv[5][u];
+            const float do_pre = d * kc[u][0];
+            const float dct = dcs[u] + d * kc[u][1] + do_pre * wco[u];
+            const float di_pre = dct * kc[u][2];
+            const float df_pre = dct * kc[u][3];
+            const float dg_pre = dct * kc[u][4];
             dpe[u][0] += di_pre * c_prev;
             dpe[u][1] += df_pre * c_prev;
             dpe[u][2] += do_pre * c_new;
@@ -802,20 +918,19 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
             for (int g = 0; g < 4; ++g) dx[u][g] = da[u][g];
             carry_new = 0.f;
           } else if constexpr (G == 3) {
-            const float r = sv[0][u], uu = sv[1][u], cand = sv[2][u], ac = sv[3][u], h_prev = sv[4][u];
-            const float du_pre = d * (cand - h_prev) * uu * (1.f - uu);
-            const float dq = clipf_(d * uu * (1.f - cand * cand), a.clip);
-            const float dr_pre = dq * ac * r * (1.f - r);
+            const float r = sv[0][u];
+            const float du_pre = d * kc[u][0];
+            const float dq = clipf_(d * kc[u][1], a.clip);
+            const float dr_pre = dq * kc[u][2];
             da[u][0] = clipf_(dr_pre, a.clip);
             da[u][1] = clipf_(du_pre, a.clip);
             da[u][2] = clipf_(dq * r, a.clip);
             dx[u][0] = da[u][0];
             dx[u][1] = da[u][1];
             dx[u][2] = dq;
-            carry_new = d * (1.f - uu);
+            carry_new = d * kc[u][3];
           } else {
-            const float h_new = sv[0][u];
-            const float dq = clipf_(d * (1.f - h_new * h_new), a.clip);
+            const float dq = clipf_(d * kc[u][0], a.clip);
             da[u][0] = dq;
             dx[u][0] = dq;
             carry_new = 0.f;
@@ -835,12 +950,18 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
         for (int g = 0; g < 4; ++g) { dx_out[u][g] = dx[u][g]; dac_out[u] = da[u][2]; dbias[u][g] += dx[u][g]; }
     }
     TC_BSTAMP(2);
-    PROXY_FENCE_SMEM();
+    if (!ldr) PROXY_FENCE_SMEM();
     TC_BSTAMP(3);
     TC_FENCE_BEFORE();
     __syncthreads();
     TC_FENCE_AFTER();
     TC_BSTAMP(4);
+    if (ldr) {
+      // stage (t - LD_P) % LD_D last held step t+1, read before the barrier above: refill it.  Then make sure
+      // step t-1 has landed: the barrier at the end of this step publishes it
+      ldr_issue(t - LD_P);
+      ldr_wait();
+    }
 
     // ---- phase B: partial dh_{t-1}[b][k] = sum_kk da[b][kk] * W_hid[k][kk], all k (MT tiles of 128 rows)
     if (warp >= 4 && warp <= 4 + MT) {
@@ -863,8 +984,8 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
     // K-major copy of this step's da for the weight-gradient GEMM and the gradient wrt the input pre-activations:
     // streamed out while the tensor core works (right after this step's proxy fence, a full step before the next
     // one, so no fence ever waits on these stores)
-    dump_aT(t, false);
-    if (own && row_ok) {
+    if (!(a.xflags & 1)) dump_aT(t, false);
+    if (own && row_ok && !(a.xflags & 2)) {
       const int64_t row = (int64_t)t * B + b0 + eb;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -876,7 +997,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
       if (G == 3) stn<NU>(a.dac + row * H + j0 + ju, dac_out);
     }
     TC_BSTAMP(5);
-    mbar_wait_cta(&mma_done, (t_end - 1 - t) & 1);
+    if (!ldr) mbar_wait_cta(&mma_done, (t_end - 1 - t) & 1);
     TC_FENCE_AFTER();
     TC_BSTAMP(6);
     {
@@ -887,23 +1008,21 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
         float v[BT], w[BT];
         tmem_ldn<BT>(tmem + 32 * mt + lane_off, v);
         tmem_ldn<BT>(tmem + 32 * mt + 16 + lane_off, w);
-        const int k = mt * 128 + quad * 32 + (tid & 31);
-        if (k < H) {
-          const int rr = k / Hs, jo = k - rr * Hs;      // owner of hidden unit k and its slot there
+        if (sb_off >= 0) {
 #pragma unroll
-          for (int b = 0; b < BT; ++b) sb[(rr * TC_BT + b) * Hs + jo] = v[b] + w[b];
+          for (int b = 0; b < BT; ++b) sb[sb_off + b * Hs] = v[b] + w[b];
         }
       }
     }
     // ---- phase C: reduce-scatter: one bulk copy of the [BT x Hs] block per peer, into slot [par][my rank]
     TC_BSTAMP(7);
-    PROXY_FENCE_SMEM();
+    if (!ldr) PROXY_FENCE_SMEM();
     TC_BSTAMP(8);
     TC_FENCE_BEFORE();
     __syncthreads();
     TC_BSTAMP(9);
     if ((tid & 31) == 0) {
-      const uint32_t bytes = (uint32_t)(TC_BT * Hs * 4);
+      const uint32_t bytes = (a.xflags & 8) ? 16u : (uint32_t)(TC_BT * Hs * 4);
       for (int rr = warp; rr < C; rr += FWD_NT / 32) {
         if (rr == rank) continue;
         const uint32_t src = sbuf_addr + (uint32_t)(par * PB + rr * TC_BT * Hs) * 4u;
@@ -911,14 +1030,10 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
         bulk_copy_to_peer(map_to_rank(dst, rr), src, bytes, map_to_rank(bar_addr[par], rr));
       }
     }
-#pragma unroll
-    for (int s = 0; s <= NSAVE; ++s)
-#pragma unroll
-      for (int u = 0; u < NU; ++u) sv[s][u] = svn[s][u];
     TC_BSTAMP(10);
   }
 #ifdef SBR_TC_TIMELINE_BUILD
-  if (a.dbg && blockIdx.x == gridDim.x - C && tid == 0) {
+  if (a.dbg && blockIdx.x == 0 && tid == 0) {
     for (int i = 0; i < 12; ++i) a.dbg[64 + i] = bph[i];
     a.dbg[76] = clock64() - bstart;
     a.dbg[77] = t_end;
@@ -926,7 +1041,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_bwd_tc_kernel(const TcArgs a) {
 #endif
 
   // ---- gradients of the learned initial states and of the peepholes
-  if (t_end > 0) {
+  if (t_end > 0 && !ldr) {
     mbar_wait_cluster(&part_full[0], n_wait[0] & 1);   // step t = 0 wrote buffer 0
   }
   if (own && row_ok) {
@@ -977,14 +1092,21 @@ TcPlan tc_plan(int G, int H) {
   // backward: MT tiles of 128 hidden rows, Kb = 4*Hs own gate columns, hi+lo: 32*MT + 2*MT*Kb TMEM columns
   p.MT = cdiv(H, 128);
   p.bwd_ok = (32 * p.MT + 2 * p.MT * 4 * p.Hs) <= 512;
-  size_t fb = (size_t)2 * 4 * p.Hs * TC_BT + (size_t)4 * p.C * TC_BT * p.Hs;
-  p.smem_bwd = std::max<size_t>(fb * sizeof(float), 120 * 1024);
+  p.smem_bwd = 0;   // depends on the tile height: tc_bwd_smem()
   return p;
 }
 
 // Rows per cluster tile.  8-row tiles halve the per-step exchange and gate math but need twice the clusters: use
 // them when all the clusters of the batch are co-resident (B = 128 -> 16 clusters x 8 CTAs = 128 of the 148 SMs).
 // SBR_TC_BT=8|16 forces a choice (tests run both).
+// backward: B operand (da hi|lo), partial-dh receive + send buffers, 4-deep staging ring of the saved tensors;
+// at least 120 KB so that a second scan CTA (one TMEM allocation each) never lands on the same SM, and small enough
+// that a side-stream GEMM CTA still fits next to it
+size_t tc_bwd_smem(const TcPlan& p, int BT) {
+  const size_t f = (size_t)2 * 4 * p.Hs * BT + (size_t)4 * p.C * BT * p.Hs + (size_t)4 * 7 * BT * p.Hs;
+  return std::max<size_t>(f * sizeof(float), 120 * 1024);
+}
+
 template <typename Kern>
 int max_active_clusters(Kern kern, const TcPlan& p, size_t smem) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1095,6 +1217,7 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   a.peep = m->params + L.peep; a.h_init = m->params + L.h_init; a.c_init = m->params + L.c_init;
   a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act; a.h_last = h_last;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
+  if (const char* e = getenv("SBR_TC_EXPERIMENT")) a.xflags = atoi(e);
   const TileSched sc = schedule_tiles(m, p, B, t_max, 0.71f);   // fwd: 2914 vs 4114 cycles per step (8 vs 16 rows)
   const int BT = sc.BT, n_tiles = sc.n_tiles;
   a.use_order = sc.use_order;
@@ -1131,7 +1254,6 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
 int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last) {
   TcPlan p = tc_plan(L.G, L.H);
   if (!p.ok || !p.bwd_ok) return 1;
-  p.smem = p.smem_bwd;
   TcArgs a{};
   a.W_hid = m->params + L.W_hid; a.peep = m->params + L.peep; a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act;
   a.dh_last = dh_last; a.dhs = dh_last ? nullptr : L.dhs; a.dXg = L.dXg; a.dac = L.dac;
@@ -1139,10 +1261,14 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   const TileSched sc = schedule_tiles(m, p, B, t_max, 0.75f);   // bwd: 4118 vs 5477 cycles per step (8 vs 16 rows)
   const int BT = sc.BT, n_tiles = sc.n_tiles;
+  p.smem = tc_bwd_smem(p, BT);
   a.use_order = sc.use_order;
   memcpy(a.order, sc.order, sizeof(a.order));
   if (L.aT && B % BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
   a.g_b = m->grads + L.b;
+  a.ld_p = 3;
+  if (const char* e = getenv("SBR_TC_LDP")) a.ld_p = std::max(1, std::min(3, atoi(e)));
+  if (const char* e = getenv("SBR_TC_EXPERIMENT")) a.xflags = atoi(e);
   if (getenv("SBR_TC_TIMELINE")) {
     static long long* bdbg = nullptr;
     static int calls = 0;
@@ -1159,8 +1285,8 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
     }
   }
 #define SBR_BWD_CASE(G_, MT_) \
-  if (L.G == G_ && p.MT == MT_ && BT == 16) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 16>, p, n_tiles, a, FWD_NT); \
-  if (L.G == G_ && p.MT == MT_ && BT == 8) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 8>, p, n_tiles, a, FWD_NT);
+  if (L.G == G_ && p.MT == MT_ && BT == 16) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 16>, p, n_tiles, a, bwd_threads(16)); \
+  if (L.G == G_ && p.MT == MT_ && BT == 8) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 8>, p, n_tiles, a, bwd_threads(8));
   SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)
 #undef SBR_BWD_CASE
   return 1;
