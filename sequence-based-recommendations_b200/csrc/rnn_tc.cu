@@ -24,6 +24,7 @@
 // Applicability: H % 4 == 0, H <= 240 (hi+lo copies of the K extent must fit in 512 TMEM columns),
 // otherwise launch_rnn_* falls back to the FFMA cluster kernels.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -47,7 +48,10 @@ struct TcArgs {
   float* hT; float* aT;                 // K-major pre-split copies for the tensor-core wgrad GEMM (may be null)
   float* g_b;                           // bias gradient slot (backward accumulates sum dXg itself when set)
   long long hT_part, hT_tile, aT_part, aT_tile;
-  int ld_p;                             // backward loader: steps of saved activations in flight
+  int ld_p;                             // backward: steps of saved activations in flight (TMA staging ring)
+  // 2-D tiled tensor maps over the saved tensors, box = [BT rows x Hs units]: the backward kernel streams its
+  // slice of a step with one TMA load per array (async proxy: nothing for the thread fences to wait on)
+  CUtensorMap tm_act, tm_cs, tm_hs, tm_dhs;
   int xflags;                           // SBR_TC_EXPERIMENT bit mask (timing experiments only: results are wrong)
   int use_order;                        // cluster c works on tile order[c] (longest tiles first) instead of tile c
   unsigned char order[64];
@@ -540,22 +544,22 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
 // ------------------------------------------------------------------------------------------------
 // TMEM map (MT = number of 128-row tiles of the hidden index k, Kb = 4*Hs own gate columns):
 //   D1_mt at 32*mt, D2_mt at 32*mt+16; A_mt_hi at 32*MT + mt*2*Kb, A_mt_lo right after it.
-// Threads: 8 compute warps (as in the forward kernel) + BT/8 LOADER warps.  The saved activations of a step (gates,
-// cell states, gradient from the layer above) come from global memory; when the compute threads fetched them
-// themselves, the fence.proxy.async they must execute before every MMA / bulk copy (a MEMBAR that drains the thread's
-// outstanding loads) put the full L2/HBM latency of that prefetch on the per-step critical path (measured: 0.33 ->
-// 0.22 ms for the whole scan without the loads).  The loader warps never fence: they issue the 16-byte loads of step
-// t-3 while step t runs, park them in registers for one step, and drop them into a double-buffered shared staging
-// area that the compute threads read with plain LDS.
-constexpr int bwd_threads(int BT) { return FWD_NT + 32 * (BT / 8); }
+// The saved activations of a step (gates, cell states, gradient from the layer above) come from global memory.  When
+// the compute threads fetched them with ordinary loads, the fence.proxy.async every thread executes before the MMA
+// and before the bulk copies (a MEMBAR that drains the thread's outstanding loads) put the full L2/HBM latency of
+// that prefetch on the per-step critical path (0.33 -> 0.22 ms for the whole scan without the loads).  They are now
+// streamed by the TMA engine: one elected thread issues one 2-D tiled load per array ([BT rows x Hs units] box) three
+// steps ahead into a 4-stage shared-memory ring, completion lands on an mbarrier, and the compute threads read the
+// stage with plain LDS.
+constexpr int bwd_threads(int) { return FWD_NT; }
 
 template <int G, int MT, int BT>
-__global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr int TC_BT = BT;
   constexpr int TPR = FWD_NT / BT;
   constexpr int NU = 32 / TPR;
   constexpr int QB = BT / 4;
-  constexpr int NLT = 32 * (BT / 8);     // loader threads
+
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int rank = cluster.block_rank();
@@ -579,7 +583,8 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const Tc
   const int PB = C * TC_BT * Hs;                // floats per part / send buffer
   float* stag = sbuf + 2 * PB;                  // [4][7][BT][Hs] saved tensors of a step, filled by the loader warps
   const int SGB = 7 * TC_BT * Hs;
-  const bool ldr = tid >= FWD_NT;               // loader warp(s): no MMA, no gate math, no fences
+  constexpr bool ldr = false;                   // (no loader warps: the TMA engine streams the saved tensors)
+  __shared__ __align__(8) uint64_t sv_full[4];
   __shared__ __align__(8) uint64_t part_full[2];
   __shared__ __align__(8) uint64_t mma_done;
   __shared__ uint32_t tmem_base_s;
@@ -591,6 +596,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const Tc
     mbar_init(&part_full[0], 1);
     mbar_init(&part_full[1], 1);
     mbar_init(&mma_done, MT + 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&sv_full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -726,70 +732,38 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const Tc
 #pragma unroll
     for (int u = 0; u < NU; ++u) sv[s][u] = 0.f;
 
-  // ---- loader: lane <-> up to two (row, unit quad) pairs of the CTA's [BT x Hs] slice; one 16-byte cp.async per
-  //      array straight into the staging ring (LD_D stages, LD_P steps ahead: the activations come back from HBM
-  //      with ~2 us latency under load, i.e. more than one step)
-  constexpr int LNP = 2;                           // BT * (Hs/4) <= BT * 8 pairs over 32 * BT/8 loader threads
+  // ---- TMA staging ring: LD_D stages, LD_P steps ahead (the activations come back from HBM with ~2 us latency
+  //      under load, i.e. more than one step)
   constexpr int LD_D = 4;
-  const int LD_P = a.ld_p;                          // 1 .. LD_D - 1 steps ahead
-  auto ldr_wait = [&]() {                           // all but the LD_P - 1 most recent groups have landed
-    switch (LD_P) {
-      case 1: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-      case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-      case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-      case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-      case 5: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-      case 6: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-      default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-    }
+  const int LD_P = a.ld_p;                          // 1 .. 3
+  const int AS = TC_BT * Hs;                        // floats per array per stage (multiple of 32: 128-byte aligned)
+  auto tma2d = [](float* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
   };
-  int l_b[LNP], l_soff[LNP];
-  long long l_g4[LNP], l_g1[LNP];                  // element offsets into [rows x 4H] / [rows x H] arrays
-  bool l_ok[LNP];
-  if (ldr) {
-    const int HQ = Hs >> 2;
+  auto ldr_issue = [&](int t) {      // executed by ONE thread
+    if (t < 0 || (a.xflags & 128)) return;
+    float* sg = stag + (t & (LD_D - 1)) * SGB;
+    uint64_t* bar = &sv_full[t & (LD_D - 1)];
+    mbar_arrive_expect_tx(bar, (uint32_t)(NA * AS * 4));
+    const int r = t * B + b0;
+    if constexpr (G == 4) {
 #pragma unroll
-    for (int pp = 0; pp < LNP; ++pp) {
-      const int pair = (tid - FWD_NT) + pp * NLT;
-      const int b = pair / HQ, q = pair - b * HQ;
-      l_ok[pp] = b < TC_BT && 4 * q < nj && b0 + b < B;
-      l_b[pp] = l_ok[pp] ? b : 0;
-      l_soff[pp] = b * Hs + 4 * q;
-      l_g4[pp] = (long long)(b0 + b) * 4 * H + j0 + 4 * q;
-      l_g1[pp] = (long long)(b0 + b) * H + j0 + 4 * q;
+      for (int g = 0; g < 4; ++g) tma2d(sg + g * AS, &a.tm_act, g * H + j0, r, bar);
+      tma2d(sg + 4 * AS, &a.tm_cs, j0, r, bar);
+      tma2d(sg + 5 * AS, &a.tm_cs, j0, r + B, bar);
+    } else if constexpr (G == 3) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tma2d(sg + g * AS, &a.tm_act, g * H + j0, r, bar);
+      tma2d(sg + 4 * AS, &a.tm_hs, j0, r, bar);
+    } else {
+      tma2d(sg, &a.tm_hs, j0, r + B, bar);
     }
-  }
-  auto cp16 = [](float* dst, const float* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
-  };
-  auto ldr_issue = [&](int t) {      // one commit group per step, empty when t < 0
-    if (t >= 0 && !(a.xflags & 128)) {
-      float* sg = stag + (t & (LD_D - 1)) * SGB;
-#pragma unroll
-      for (int pp = 0; pp < LNP; ++pp) {
-        if (!(l_ok[pp] && t < lens_s[l_b[pp]])) continue;
-        const long long r4 = (long long)t * B * 4 * H + l_g4[pp], r1 = (long long)t * B * H + l_g1[pp];
-        float* d = sg + l_soff[pp];
-        const int AS = TC_BT * Hs;
-        if constexpr (G == 4) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) cp16(d + g * AS, a.act + r4 + g * H);
-          cp16(d + 4 * AS, a.cs + r1);
-          cp16(d + 5 * AS, a.cs + r1 + (long long)B * H);
-        } else if constexpr (G == 3) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) cp16(d + g * AS, a.act + r4 + g * H);
-          cp16(d + 4 * AS, a.hs + r1);
-        } else {
-          cp16(d, a.hs + r1 + (long long)B * H);
-        }
-        if (a.dhs) cp16(d + NSAVE * AS, a.dhs + r1);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (a.dhs) tma2d(sg + NSAVE * AS, &a.tm_dhs, j0, r, bar);
   };
   // compute threads: this step's saved tensors out of the staging buffer (rows past their length are never used)
   auto fetch_saved = [&](int t) {
+    if (!(a.xflags & 128)) mbar_wait_cta(&sv_full[t & (LD_D - 1)], ((t_end - 1 - t) >> 2) & 1);
     if (own && t < lens_s[eb]) {
       const float* sg = stag + (t & (LD_D - 1)) * SGB + eb * Hs + ju;
 #pragma unroll
@@ -797,11 +771,9 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const Tc
         if (s2 < NA) ldn<NU>(sg + s2 * TC_BT * Hs, sv[s2]);
     }
   };
-  if (ldr) {
-    // LD_P steps in flight; the first one must have landed before the loop starts (the cluster barrier below
-    // publishes it to the compute threads)
+  if (tid == FWD_NT - 32) {     // lane 0 of warp 7 (the one compute warp that never issues MMAs)
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&a.tm_act) : "memory");
     for (int i = 1; i <= LD_P; ++i) ldr_issue(t_end - i);
-    ldr_wait();
   }
 
   // one phase of part_full[x] = the partial dh blocks of my units have landed from the C-1 other CTAs
@@ -956,12 +928,8 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const Tc
     __syncthreads();
     TC_FENCE_AFTER();
     TC_BSTAMP(4);
-    if (ldr) {
-      // stage (t - LD_P) % LD_D last held step t+1, read before the barrier above: refill it.  Then make sure
-      // step t-1 has landed: the barrier at the end of this step publishes it
-      ldr_issue(t - LD_P);
-      ldr_wait();
-    }
+    // stage (t - LD_P) % LD_D last held step t+1, which every thread read before the barrier above: refill it
+    if (tid == FWD_NT - 32) ldr_issue(t - LD_P);
 
     // ---- phase B: partial dh_{t-1}[b][k] = sum_kk da[b][kk] * W_hid[k][kk], all k (MT tiles of 128 rows)
     if (warp >= 4 && warp <= 4 + MT) {
@@ -1099,6 +1067,38 @@ TcPlan tc_plan(int G, int H) {
 // Rows per cluster tile.  8-row tiles halve the per-step exchange and gate math but need twice the clusters: use
 // them when all the clusters of the batch are co-resident (B = 128 -> 16 clusters x 8 CTAs = 128 of the 148 SMs).
 // SBR_TC_BT=8|16 forces a choice (tests run both).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// row-major fp32 matrix [rows x cols] -> 2-D tiled map with a [box_rows x box_cols] box, no swizzle, OOB reads = 0
+bool make_map2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  if (!fn || !base) return false;
+  // the maps only depend on the allocation and the box: encode once (cuTensorMapEncodeTiled costs ~10 us of host time)
+  struct Key { const float* base; uint64_t rows, cols; uint32_t bc, br; CUtensorMap tm; };
+  static std::vector<Key> cache;
+  for (const Key& k : cache)
+    if (k.base == base && k.rows == rows && k.cols == cols && k.bc == box_cols && k.br == box_rows) { *tm = k.tm; return true; }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  if (fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 256) cache.clear();   // allocations of destroyed handles
+  cache.push_back(Key{base, rows, cols, box_cols, box_rows, *tm});
+  return true;
+}
+
 // backward: B operand (da hi|lo), partial-dh receive + send buffers, 4-deep staging ring of the saved tensors;
 // at least 120 KB so that a second scan CTA (one TMEM allocation each) never lands on the same SM, and small enough
 // that a side-stream GEMM CTA still fits next to it
@@ -1186,8 +1186,18 @@ TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, 
 
 template <typename Kern>
 int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArgs& args, int threads = TC_NT) {
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e != cudaSuccess) { sbr_set_error(m, SBR_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SBR_E_CUDA; }
+  cudaError_t e = cudaSuccess;
+  // raise the opt-in shared-memory limit once per kernel, not on every launch (Kern is the same function-pointer
+  // TYPE for every instantiation, so the cache is keyed by the pointer value)
+  static std::vector<std::pair<const void*, size_t>> smem_set;
+  size_t* have = nullptr;
+  for (auto& kv : smem_set) if (kv.first == (const void*)kern) have = &kv.second;
+  if (!have) { smem_set.push_back({(const void*)kern, 0}); have = &smem_set.back().second; }
+  if (p.smem > *have) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) { sbr_set_error(m, SBR_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SBR_E_CUDA; }
+    *have = p.smem;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.C * n_tiles, 1, 1);
   cfg.blockDim = dim3(threads, 1, 1);
@@ -1266,6 +1276,16 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   memcpy(a.order, sc.order, sizeof(a.order));
   if (L.aT && B % BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
   a.g_b = m->grads + L.b;
+  {
+    // tensor maps over the whole allocations ([T*Bmax (+Bmax)] rows): box = [BT x Hs]
+    const uint64_t TB = (uint64_t)m->T * m->B;
+    bool ok = true;
+    if (L.G > 1) ok = ok && make_map2d(&a.tm_act, L.act, TB, 4 * (uint64_t)L.H, p.Hs, BT);
+    if (L.G == 4) ok = ok && make_map2d(&a.tm_cs, L.cs, TB + m->B, L.H, p.Hs, BT);
+    ok = ok && make_map2d(&a.tm_hs, L.hs, TB + m->B, L.H, p.Hs, BT);
+    if (a.dhs) ok = ok && make_map2d(&a.tm_dhs, L.dhs, TB, L.H, p.Hs, BT);
+    if (!ok) { sbr_set_error(m, SBR_E_CUDA, "cuTensorMapEncodeTiled failed (H=%d Hs=%d BT=%d)", L.H, p.Hs, BT); return SBR_E_CUDA; }
+  }
   a.ld_p = 3;
   if (const char* e = getenv("SBR_TC_LDP")) a.ld_p = std::max(1, std::min(3, atoi(e)));
   if (const char* e = getenv("SBR_TC_EXPERIMENT")) a.xflags = atoi(e);
