@@ -469,26 +469,34 @@ extern "C" int sbr_set_skip_update(sbr_model* m, int flag) {
 // ------------------------------------------------------------------------------------------------
 // mask [B,T] float -> lengths; rejects anything that is not a left-aligned run of ones
 static int mask_to_len(sbr_model* m, const float* mask, const int32_t* X, int B, int* t_max) {
+  // on the per-step host path: the scans below are written as branch-free reductions so that the compiler vectorises
+  // them; the slow, index-reporting loops only run once something is wrong
   int mx = 0;
   const int T = m->T, K = m->K;
+  const uint32_t n_in = (uint32_t)m->n_in;
   for (int b = 0; b < B; ++b) {
-    const float* r = mask + (size_t)b * T;
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(mask + (size_t)b * T);
     int L = 0;
-    while (L < T && r[L] != 0.f) ++L;
-    for (int t = L; t < T; ++t)
-      if (r[t] != 0.f) {
-        sbr_set_error(m, SBR_E_MASK, "mask row %d is not a left-aligned run of ones (hole at %d)", b, L);
-        return SBR_E_MASK;
-      }
+    while (L < T && (r[L] & 0x7fffffffu) != 0u) ++L;      // != 0.f  (-0.f counts as zero)
+    uint32_t tail = 0;
+    for (int t = L; t < T; ++t) tail |= r[t] & 0x7fffffffu;
+    if (tail) {
+      sbr_set_error(m, SBR_E_MASK, "mask row %d is not a left-aligned run of ones (hole at %d)", b, L);
+      return SBR_E_MASK;
+    }
     m->h_len[b] = L;
     mx = std::max(mx, L);
     if (X) {
       const int32_t* x = X + (size_t)b * T * K;
-      for (int i = 0; i < L * K; ++i)
-        if (x[i] < 0 || x[i] >= m->n_in) {
-          sbr_set_error(m, SBR_E_RANGE, "X[%d,%d,%d] = %d outside [0,%d)", b, i / K, i % K, x[i], m->n_in);
-          return SBR_E_RANGE;
-        }
+      const int n = L * K;
+      uint32_t bad = 0;
+      for (int i = 0; i < n; ++i) bad |= (uint32_t)((uint32_t)x[i] >= n_in);   // negative ids wrap to huge values
+      if (bad)
+        for (int i = 0; i < n; ++i)
+          if (x[i] < 0 || (uint32_t)x[i] >= n_in) {
+            sbr_set_error(m, SBR_E_RANGE, "X[%d,%d,%d] = %d outside [0,%d)", b, i / K, i % K, x[i], m->n_in);
+            return SBR_E_RANGE;
+          }
     }
   }
   *t_max = mx;

@@ -52,6 +52,7 @@ struct TcArgs {
   // 2-D tiled tensor maps over the saved tensors, box = [BT rows x Hs units]: the backward kernel streams its
   // slice of a step with one TMA load per array (async proxy: nothing for the thread fences to wait on)
   CUtensorMap tm_act, tm_cs, tm_hs, tm_dhs;
+  CUtensorMap tm_xg;                    // forward: input pre-activations Xg [rows x G*H]
   int xflags;                           // SBR_TC_EXPERIMENT bit mask (timing experiments only: results are wrong)
   int use_order;                        // cluster c works on tile order[c] (longest tiles first) instead of tile c
   unsigned char order[64];
@@ -205,7 +206,7 @@ constexpr int FWD_NT = 256;  // forward: 8 warps (warp w reaches TMEM lane quadr
 // columns are never read), so the exchange moves half the bytes, every thread owns ONE unit of the gate math, and a
 // batch of 128 rows spreads over 16 clusters = 128 SMs instead of 64.
 template <int G, int BT>
-__global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr int TC_BT = BT;
   constexpr int TPR = FWD_NT / BT;     // threads per batch row
   constexpr int NU = 32 / TPR;         // hidden units per thread (Hs <= 32)
@@ -230,6 +231,11 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   float* hbuf = smem;
   const int HB = Kp * TC_BT * 2;                 // floats per buffer (Kp/4 blocks of 128 floats)
   float* gsm = hbuf + 2 * HB;                    // [16][GSM_LD] gate pre-activations, row b, column m = 4j+g
+  // input pre-activations Xg of the CTA's slice, streamed by the TMA engine 3 steps ahead: ring [4][G][BT][Hs]
+  // (ordinary prefetch loads would be drained by the fence.proxy.async before the h exchange, see the backward)
+  float* xs = gsm + TC_BT * GSM_LD;
+  const int XAS = TC_BT * Hs, XSB = G * XAS;
+  __shared__ __align__(8) uint64_t x_full[4];
   __shared__ __align__(8) uint64_t raw_full[2];
   __shared__ __align__(8) uint64_t mma_done;
   __shared__ uint32_t tmem_base_s;
@@ -247,6 +253,7 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
     mbar_init(&raw_full[0], 1);
     mbar_init(&raw_full[1], 1);
     mbar_init(&mma_done, 3);
+    for (int i = 0; i < 4; ++i) mbar_init(&x_full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -329,16 +336,26 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
       if (G == 4) a.cs[(int64_t)(b0 + eb) * H + j0 + ju + u] = a.c_init[j0 + ju + u];
     }
   }
-  float xc[G][NU], xn[G][NU];
+  float xc[G][NU];
 #pragma unroll
   for (int g = 0; g < G; ++g)
 #pragma unroll
-    for (int u = 0; u < NU; ++u) xc[g][u] = xn[g][u] = 0.f;
-  auto load_x = [&](int t, float (&x)[G][NU]) {
-    if (own && t < lens_s[eb]) {
-      const float* src = a.Xg + ((int64_t)t * B + b0 + eb) * GH + j0 + ju;
+    for (int u = 0; u < NU; ++u) xc[g][u] = 0.f;
+  auto x_issue = [&](int t) {        // executed by ONE thread: G boxes [BT rows x Hs units] of step t
+    float* dst = xs + (t & 3) * XSB;
+    mbar_arrive_expect_tx(&x_full[t & 3], (uint32_t)(XSB * 4));
 #pragma unroll
-      for (int g = 0; g < G; ++g) ldgn<NU>(src + g * H, x[g]);
+    for (int g = 0; g < G; ++g)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                   :: "r"(smem_u32(dst + g * XAS)), "l"(&a.tm_xg), "r"(smem_u32(&x_full[t & 3])), "r"(g * H + j0), "r"(t * B + b0)
+                   : "memory");
+  };
+  auto x_fetch = [&](int t, float (&x)[G][NU]) {
+    mbar_wait_cta(&x_full[t & 3], (t >> 2) & 1);
+    if (own && t < lens_s[eb]) {
+      const float* src = xs + (t & 3) * XSB + eb * Hs + ju;
+#pragma unroll
+      for (int g = 0; g < G; ++g) ldn<NU>(src + g * XAS, x[g]);
     }
   };
   PROXY_FENCE_SMEM();       // hbuf was written through the generic proxy
@@ -346,7 +363,10 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
   __syncthreads();
   TC_FENCE_AFTER();
   const int t_end = t_end_s;
-  if (t_end > 0) load_x(0, xc);
+  if (tid == FWD_NT - 32 && !(a.xflags & 16)) {     // lane 0 of warp 7 (never issues MMAs)
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&a.tm_xg) : "memory");
+    for (int t = 0; t < 3 && t < t_end; ++t) x_issue(t);
+  }
   // K-major copy of the own slice of a state block (hi and lo) for the weight-gradient GEMM: one 16-byte chunk =
   // (part, unit, 4 consecutive rows); `blk` = index of the hs block (0 = learned init, t+1 = state after step t)
   auto dump_hT = [&](const float* buf, int blk) {
@@ -406,8 +426,12 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
       __syncwarp();
     }
     TC_STAMP(3);
-    // input pre-activations of the NEXT step: in flight while the tensor core works
-    if (t + 1 < t_end && !(a.xflags & 16)) load_x(t + 1, xn);
+    // stage (t + 3) % 4 was last read in the gate math of step t-1, before the barrier that ended it: refill it;
+    // then this step's input pre-activations (landed steps ago) while the tensor core works
+    if (!(a.xflags & 16)) {
+      if (tid == FWD_NT - 32 && t + 3 < t_end) x_issue(t + 3);
+      x_fetch(t, xc);
+    }
     mbar_wait_cta(&mma_done, t & 1);
     TC_STAMP(4);
     TC_FENCE_AFTER();
@@ -507,10 +531,6 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const TcArgs a) {
       }
     }
     if (!(a.xflags & 64)) dump_hT(hbuf + nxt * HB, t + 1);
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int u = 0; u < NU; ++u) xc[g][u] = xn[g][u];
     TC_STAMP(7);
   }
 
@@ -1055,7 +1075,7 @@ TcPlan tc_plan(int G, int H) {
   }
   if (!p.ok) return p;
   constexpr int TC_BT = 16;   // sized for the larger tile; the 8-row tile needs half
-  size_t f = (size_t)4 * p.Kp * TC_BT + (size_t)TC_BT * GSM_LD;
+  size_t f = (size_t)4 * p.Kp * TC_BT + (size_t)TC_BT * GSM_LD + (size_t)4 * 4 * TC_BT * p.Hs;
   p.smem = std::max<size_t>(f * sizeof(float), 120 * 1024);   // > half an SM: one CTA (one TMEM allocation) per SM
   // backward: MT tiles of 128 hidden rows, Kb = 4*Hs own gate columns, hi+lo: 32*MT + 2*MT*Kb TMEM columns
   p.MT = cdiv(H, 128);
@@ -1230,6 +1250,10 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   if (const char* e = getenv("SBR_TC_EXPERIMENT")) a.xflags = atoi(e);
   const TileSched sc = schedule_tiles(m, p, B, t_max, 0.71f);   // fwd: 2914 vs 4114 cycles per step (8 vs 16 rows)
   const int BT = sc.BT, n_tiles = sc.n_tiles;
+  if (!make_map2d(&a.tm_xg, L.Xg, (uint64_t)m->T * m->B, (uint64_t)L.G * L.H, p.Hs, BT)) {
+    sbr_set_error(m, SBR_E_CUDA, "cuTensorMapEncodeTiled failed (Xg, H=%d Hs=%d BT=%d)", L.H, p.Hs, BT);
+    return SBR_E_CUDA;
+  }
   a.use_order = sc.use_order;
   memcpy(a.order, sc.order, sizeof(a.order));
   if (L.hT && B % BT == 0) { a.hT = L.hT; a.hT_part = L.hT_part; a.hT_tile = L.hT_tile; }
