@@ -94,6 +94,9 @@ struct sbr_model {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // off-critical-path work (see side_fork / side_join in model.cu)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_staged = nullptr;    // the H2D copies out of the pinned staging buffers have completed
+  cudaEvent_t ev_cost = nullptr;      // the step's cost has landed in h_cost (recorded right after the loss kernels)
+  bool cost_early = false;            // this step's cost was copied out early: finish_step() waits on ev_cost only
   bool side_pending = false;
   int deferred_out_B = 0;             // >0: output-layer weight gradients still to be launched on the side stream
   bool staging_in_flight = false;     // pinned staging buffers still feed an H2D copy

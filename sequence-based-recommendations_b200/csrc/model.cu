@@ -231,6 +231,8 @@ extern "C" void sbr_destroy(sbr_model* m) {
   if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->ev_staged) cudaEventDestroy(m->ev_staged);
+  if (m->ev_cost) cudaEventDestroy(m->ev_cost);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -256,6 +258,8 @@ static int create_impl(sbr_model* m) {
   }
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  CU_TRY(m, cudaEventCreateWithFlags(&m->ev_staged, cudaEventDisableTiming));
+  CU_TRY(m, cudaEventCreateWithFlags(&m->ev_cost, cudaEventDisableTiming));
   for (auto& e : m->ev) CU_TRY(m, cudaEventCreate(&e));
   build_layout(m);
 
@@ -504,8 +508,8 @@ static int mask_to_len(sbr_model* m, const float* mask, const int32_t* X, int B,
 }
 
 static int stage_common(sbr_model* m, BatchSlot& s, const int32_t* X, const float* mask, int B) {
-  if (m->staging_in_flight) {
-    CU_TRY(m, cudaStreamSynchronize(m->stream));
+  if (m->staging_in_flight) {   // the previous batch must have left the pinned staging buffers (normally long ago)
+    CU_TRY(m, cudaEventSynchronize(m->ev_staged));
     m->staging_in_flight = false;
   }
   if (B < 1 || B > m->B) { sbr_set_error(m, SBR_E_ARG, "B=%d outside [1,%d]", B, m->B); return SBR_E_ARG; }
@@ -521,8 +525,8 @@ static int stage_common(sbr_model* m, BatchSlot& s, const int32_t* X, const floa
   memcpy(m->h_stage, X, xbytes);
   CU_TRY(m, cudaMemcpyAsync(s.X, m->h_stage, xbytes, cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaMemcpyAsync(s.len, m->h_len, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
-  // the pinned staging buffers are reused by the next call: it must not start before these copies have left
-  // them.  Every path that returns a cost synchronises the stream at its end, so no extra sync is paid here.
+  // the pinned staging buffers are reused by the next call: it must not start before these copies have left them
+  CU_TRY(m, cudaEventRecord(m->ev_staged, m->stream));
   m->staging_in_flight = true;
   return 0;
 }
@@ -732,10 +736,21 @@ static int finish_step(sbr_model* m, float* cost) {
     }
   }
   stage_mark(m, 8);
-  if (cost) CU_TRY(m, cudaMemcpyAsync(m->h_cost, m->grads + m->cost_slot, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  if (cost && !m->cost_early)
+    CU_TRY(m, cudaMemcpyAsync(m->h_cost, m->grads + m->cost_slot, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   if (!m->skip_update)
     if ((rc = launch_optimizer(m))) return rc;
   stage_mark(m, 9);
+  if (m->cost_early && cost) {
+    // the cost left the device right after the loss kernels: return as soon as it has landed.  The backward pass
+    // and the update keep running; everything the caller can do next (another step, get/set_param, scores) is
+    // ordered behind them on the same stream, and the host work of the next step overlaps them.
+    m->cost_early = false;
+    CU_TRY(m, cudaEventSynchronize(m->ev_cost));
+    *cost = m->h_cost[0];
+    return 0;
+  }
+  m->cost_early = false;
   if (cost || m->profiling) {
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     m->staging_in_flight = false;
@@ -757,6 +772,12 @@ static int step_cce(sbr_model* m, const BatchSlot& s, float* cost) {
   if (m->cfg.regularization != 0.f)
     if ((rc = launch_bias_reg(m, m->params + m->out_b, m->grads + m->out_b, N, m->cfg.regularization / (float)m->cfg.n_ranks,
                               m->grads + m->cost_slot))) return rc;
+  // single rank: the cost is final here (no all-reduce): start its way to the host now, before the backward pass
+  if (cost && !m->nccl_comm && !m->profiling && !getenv("SBR_NO_EARLY_COST")) {
+    CU_TRY(m, cudaMemcpyAsync(m->h_cost, m->grads + m->cost_slot, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaEventRecord(m->ev_cost, m->stream));
+    m->cost_early = true;
+  }
   if ((rc = output_backward_full(m, B))) return rc;
   stage_mark(m, 4);
   if ((rc = backward_stack(m, s))) return rc;
@@ -781,7 +802,8 @@ extern "C" int sbr_train_step_cce(sbr_model* m, const int32_t* X, const float* m
   int rc;
   if ((rc = begin_step(m))) return rc;
   stage_mark(m, 0);
-  // the caller's buffers stay valid until this call returns, and it returns only after the stream has drained
+  // X goes through the pinned staging buffer, Y / pop are small pageable copies that the driver stages at call
+  // time: the caller's buffers are free when this call returns even though the device may still be working
   if ((rc = stage_cce_impl(m, 0, X, mask, Y, pop, B, false))) return rc;
   float local_cost;
   return step_cce(m, m->slots[0], cost ? cost : &local_cost);
