@@ -372,7 +372,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    kern = {"rnn_fwd": "rnn_fwd_tc_kernel<4>", "rnn_bwd": "rnn_bwd_tc_kernel<4,2>"}[dom] if cfg["cell"] == "LSTM" else dom
+    kern = {"rnn_fwd": "rnn_fwd_tc_kernel<4,8>", "rnn_bwd": "rnn_bwd_tc_kernel<4,2,8>"}[dom] if cfg["cell"] == "LSTM" else dom
     roofline = {"kernel": kern, "stage": dom, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "math": "3xTF32 on tcgen05 (fp32-accurate): 3 MMA passes at the TF32 rate = 1/6 of the bf16 peak per "
