@@ -267,6 +267,8 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ B200 arm
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"       # stdout carries exactly one JSON line (NCCL prints its banner there)
     from sbr_b200 import _capi
     dist = None
     nccl_id = None

@@ -29,6 +29,15 @@ class RNNOneHot(rnn.RNNBase):
             return self.engine.train_step_cce(sl(X), sl(mask), sl(Y), sl(pop))
         self.train_function = train_function
 
+    def _split_rows(self, arr):
+        """This rank's rows of a global-batch array: row r goes to rank r % n_ranks.  The batch builder emits rows in
+        ascending length (nested prefixes), so a contiguous split would hand the last rank the longest sequences on
+        every step and the other ranks would sit in the all-reduce waiting for it.  The CCE loss is a plain sum over
+        rows, so any partition gives the same gradient."""
+        if self.n_ranks == 1:
+            return arr
+        return np.ascontiguousarray(arr[self.rank::self.n_ranks])
+
     def _prepare_input(self, sequences):
         """(X, mask, Y, pop, exclude) for a list of [user_id, input_sequence, targets]
         (rnn_one_hot.py:83-106); `exclude` is the ragged list of seen ids instead of a dense [B,N]."""
