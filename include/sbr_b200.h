@@ -112,7 +112,9 @@ SBR_API int sbr_reset_optimizer(sbr_model* m);                    /* zero the up
 SBR_API int sbr_set_skip_update(sbr_model* m, int flag);          /* 1: steps compute cost+gradients only (tests) */
 
 /* ---- train_function --------------------------------------------------------------------- */
-/* RNNOneHot: cost = mean_b(-log softmax(h W + b)[Y_b] / pop_b) (+ bias reg), rnn_one_hot.py:65-77 */
+/* RNNOneHot: cost = mean_b(-log softmax(h W + b)[Y_b] / pop_b) (+ bias reg), rnn_one_hot.py:65-77.
+ * On a single rank the call returns as soon as the cost is on the host; the backward pass and the update may still
+ * be running on the handle's stream (every later call on the handle is ordered behind them). */
 SBR_API int sbr_train_step_cce(sbr_model* m, const int32_t* X, const float* mask, const int32_t* Y,
                        const float* pop, int B, float* cost);
 /* RNNSampling: cells = [Y_all; samples], rnn_sampling.py:68-91,137 and sparse_lstm.py:41-54.

@@ -2,26 +2,33 @@
 // per-step gate GEMM on tcgen05.mma, fp32-accurate through the 3xTF32 split.
 //
 // Same reference semantics as rnn_cluster.cu (sparse_lstm.py:377-425, :764-805, :1120-1152) and the
-// same ownership: a cluster of C CTAs owns a tile of 16 batch rows for all T steps; CTA r owns the
+// same ownership: a cluster of C CTAs owns a tile of BT = 8 or 16 batch rows for all T steps; CTA r owns the
 // hidden units [r*Hs, (r+1)*Hs) of every gate.  What changes is how a step is computed:
 //
 //   * the CTA's slice of W_hid is the **A operand, resident in TMEM** for the whole scan
 //     (tcgen05.st once): row m = 4*j + g (unit j, gate g) of a 128-row tile, K along the columns,
-//     stored twice -- hi = top 19 bits (what kind::tf32 reads), lo = w - hi;
-//   * h_{t-1} (forward) / da_t (backward) is the **B operand in shared memory** [k/4][16 rows][4]
-//     (K-major, no swizzle: 8x16B core matrices, SBO 128 B, LBO 256 B), also as hi/lo;
-//   * D[128 x 16] += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, fp32 accumulators in TMEM, issued by one thread;
-//     tcgen05.commit -> mbarrier -> tcgen05.ld (each thread = one gate row, 16 batch columns);
-//   * the fused gate math runs on (row, 4 consecutive units) per thread, so every state exchange
-//     is 16-byte: h_t quads are stored straight into the shared memory of all CTAs of the cluster
-//     (DSMEM, fp32) and announced with one remote mbarrier.arrive(release.cluster) per warp --
-//     no cluster-wide barrier in the loop; the receiver splits hi/lo locally.
+//     stored twice -- hi = fp32 rounded to the 19 bits kind::tf32 reads, lo = w - hi;
+//   * h_{t-1} (forward) / da_t (backward) is the **B operand in shared memory** [k/4][hi|lo][BT rows][4]
+//     (K-major, no swizzle: 8x16B core matrices), already split hi/lo by its producer;
+//   * D[128 x 16] = A_hi*B_hi, A_hi*B_lo, A_lo*B_hi in separate fp32 TMEM accumulators, one accumulation chain per
+//     issuing warp (elect.sync); tcgen05.commit -> mbarrier -> tcgen05.ld (thread = gate row) -> shared memory;
+//   * the fused gate math runs on one (row, unit) [8-row tiles] or (row, 2 units) [16-row tiles] per thread; the
+//     new h_t slice is written pre-split into the local copy of the next B operand and sent to every peer CTA
+//     with ONE bulk copy (cp.async.bulk shared::cta -> shared::cluster) that completes on the peer's mbarrier:
+//     no cluster-wide barrier in the loop, no receiver-side work;
+//   * the per-step inputs from global memory (Xg forward; saved gates / cell states / upstream gradient backward)
+//     are streamed by the TMA engine (cp.async.bulk.tensor.2d, 4-stage ring, 3 steps ahead) so that the
+//     fence.proxy.async every thread executes before the MMA never has an outstanding global load to drain.
 //
 // The backward keeps W_hid^T-style tiles in TMEM (rows = hidden index k, columns = own gate columns):
 // dh_{t-1}[b][k] partial = sum over OWN gate columns of da[b][gj] W_hid[k][gj] (split-K), reduce-
-// scattered to the owners through DSMEM like rnn_cluster.cu.
+// scattered to the owners with bulk copies.  It also writes the K-major hi/lo copies of da (and the forward those of
+// h) that wgrad_tc.cu contracts, and accumulates the bias gradient.
 //
-// Applicability: H % 4 == 0, H <= 240 (hi+lo copies of the K extent must fit in 512 TMEM columns),
+// Host side: schedule_tiles() orders the tiles longest-first and chooses the tile height from the host copy of the
+// lengths (15 eight-CTA clusters are co-resident on a B200; a batch of 128 rows is 16 eight-row tiles).
+//
+// Applicability: H % 4 == 0, H <= 224 (hi+lo copies of the K extent must fit in 512 TMEM columns),
 // otherwise launch_rnn_* falls back to the FFMA cluster kernels.
 #include <cooperative_groups.h>
 #include <cuda.h>
@@ -33,7 +40,6 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int TC_NT = 128;   // 4 warps: TMEM lane quadrants 0..3
 constexpr int TC_N = 16;     // MMA N (minimum for M = 128); the cluster tile holds BT = 16 or 8 live batch rows
 constexpr int GSM_LD = 132;  // padded row of the gate staging buffer
 
@@ -1205,7 +1211,7 @@ TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, 
 }
 
 template <typename Kern>
-int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArgs& args, int threads = TC_NT) {
+int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArgs& args, int threads) {
   cudaError_t e = cudaSuccess;
   // raise the opt-in shared-memory limit once per kernel, not on every launch (Kern is the same function-pointer
   // TYPE for every instantiation, so the cache is keyed by the pointer value)
