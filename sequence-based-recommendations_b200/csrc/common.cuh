@@ -94,6 +94,8 @@ struct sbr_model {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // off-critical-path work (see side_fork / side_join in model.cu)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux = nullptr;         // second scan launch of a mixed 8-/16-row tiling (rnn_tc.cu), concurrent with the first
+  cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
   cudaEvent_t ev_staged = nullptr;    // the H2D copies out of the pinned staging buffers have completed
   cudaEvent_t ev_cost = nullptr;      // the step's cost has landed in h_cost (recorded right after the loss kernels)
   bool cost_early = false;            // this step's cost was copied out early: finish_step() waits on ev_cost only

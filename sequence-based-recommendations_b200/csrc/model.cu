@@ -232,6 +232,9 @@ extern "C" void sbr_destroy(sbr_model* m) {
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
   if (m->ev_staged) cudaEventDestroy(m->ev_staged);
+  if (m->ev_aux_fork) cudaEventDestroy(m->ev_aux_fork);
+  if (m->ev_aux_join) cudaEventDestroy(m->ev_aux_join);
+  if (m->aux) cudaStreamDestroy(m->aux);
   if (m->ev_cost) cudaEventDestroy(m->ev_cost);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -255,10 +258,13 @@ static int create_impl(sbr_model* m) {
     const bool prio = !getenv("SBR_NO_STREAM_PRIORITY");
     CU_TRY(m, cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prio ? hi : 0));
     CU_TRY(m, cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, prio ? lo : 0));
+    CU_TRY(m, cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, prio ? hi : 0));
   }
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_staged, cudaEventDisableTiming));
+  CU_TRY(m, cudaEventCreateWithFlags(&m->ev_aux_fork, cudaEventDisableTiming));
+  CU_TRY(m, cudaEventCreateWithFlags(&m->ev_aux_join, cudaEventDisableTiming));
   CU_TRY(m, cudaEventCreateWithFlags(&m->ev_cost, cudaEventDisableTiming));
   for (auto& e : m->ev) CU_TRY(m, cudaEventCreate(&e));
   build_layout(m);

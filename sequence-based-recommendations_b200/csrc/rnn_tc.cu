@@ -1163,7 +1163,10 @@ int resident_clusters(const TcPlan& p) {
 // the host copy of the lengths the launcher (a) sorts the tiles longest first, so that when there are more tiles
 // than slots the short ones queue behind clusters that finish early, and (b) takes 8-row tiles only when their
 // makespan (x the measured per-step cost ratio of an 8-row vs a 16-row tile) beats the 16-row tiling.
-struct TileSched { int BT; int n_tiles; int use_order; unsigned char order[64]; };
+// extra16 >= 0: MIXED tiling -- the 16-row group `extra16` (rows 16g .. 16g+15, the shortest one) runs as one 16-row
+// tile on a second stream while the remaining rows run as 8-row tiles: B = 128 is then 14 + 1 = 15 clusters, all
+// co-resident, instead of 16 eight-row tiles of which one has to queue.
+struct TileSched { int BT; int n_tiles; int use_order; unsigned char order[64]; int extra16; };
 int makespan(const int* t_end, int n, int slots) {   // t_end sorted descending
   std::vector<int> busy(std::max(1, slots), 0);
   for (int i = 0; i < n; ++i) {
@@ -1174,6 +1177,7 @@ int makespan(const int* t_end, int n, int slots) {   // t_end sorted descending
 }
 TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, float ratio8) {
   TileSched sc{};
+  sc.extra16 = -1;
   const int slots = resident_clusters(p);
   const int32_t* hl = m->cur_hlen;
   auto tiles_of = [&](int BT, int* t_end, unsigned char* order) {
@@ -1202,6 +1206,23 @@ TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, 
   if (!BT) {
     const float c8 = ratio8 * (float)makespan(t8, n8, slots), c16 = (float)makespan(t16, n16, slots);
     BT = (B % 8 == 0 && c8 < c16) ? 8 : 16;
+    // one tile too many for the co-resident slots: fold the two shortest adjacent 8-row tiles into one 16-row tile
+    const bool force_mixed = getenv("SBR_TC_FORCE_MIXED") != nullptr;     // tests
+    if (B % 16 == 0 && ((n8 == slots + 1 && !getenv("SBR_TC_NO_MIXED")) || (force_mixed && n8 >= 4))) {
+      const int g = o16[n16 - 1];                       // shortest 16-row group (t16 / o16 are sorted descending)
+      int rest = 0;
+      for (int i = 0; i < n8; ++i) if ((o8[i] >> 1) != g) rest = std::max(rest, t8[i]);
+      const float cmix = std::max(ratio8 * (float)rest, (float)t16[n16 - 1]);
+      if (cmix < std::min(c8, c16) || force_mixed) {
+        sc.BT = 8;
+        sc.use_order = 1;
+        sc.extra16 = g;
+        int n = 0;
+        for (int i = 0; i < n8; ++i) if ((o8[i] >> 1) != g) sc.order[n++] = o8[i];
+        sc.n_tiles = n;
+        return sc;
+      }
+    }
   }
   sc.BT = BT;
   sc.n_tiles = BT == 8 ? n8 : n16;
@@ -1211,7 +1232,7 @@ TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, 
 }
 
 template <typename Kern>
-int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArgs& args, int threads) {
+int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArgs& args, int threads, cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
   // raise the opt-in shared-memory limit once per kernel, not on every launch (Kern is the same function-pointer
   // TYPE for every instantiation, so the cache is keyed by the pointer value)
@@ -1228,7 +1249,7 @@ int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArg
   cfg.gridDim = dim3(p.C * n_tiles, 1, 1);
   cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = p.smem;
-  cfg.stream = m->stream;
+  cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1255,23 +1276,37 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   if (const char* e = getenv("SBR_TC_EXPERIMENT")) a.xflags = atoi(e);
   const TileSched sc = schedule_tiles(m, p, B, t_max, 0.71f);   // fwd: 2914 vs 4114 cycles per step (8 vs 16 rows)
-  const int BT = sc.BT, n_tiles = sc.n_tiles;
-  if (!make_map2d(&a.tm_xg, L.Xg, (uint64_t)m->T * m->B, (uint64_t)L.G * L.H, p.Hs, BT)) {
-    sbr_set_error(m, SBR_E_CUDA, "cuTensorMapEncodeTiled failed (Xg, H=%d Hs=%d BT=%d)", L.H, p.Hs, BT);
-    return SBR_E_CUDA;
-  }
-  a.use_order = sc.use_order;
-  memcpy(a.order, sc.order, sizeof(a.order));
-  if (L.hT && B % BT == 0) { a.hT = L.hT; a.hT_part = L.hT_part; a.hT_tile = L.hT_tile; }
+  const int BT = sc.BT;
   static long long* dbg = nullptr;
   if (getenv("SBR_TC_TIMELINE")) {
     if (!dbg) { cudaMalloc(&dbg, 80 * 8 * sizeof(long long)); cudaMemset(dbg, 0, 80 * 8 * sizeof(long long)); }
     a.dbg = dbg;
   }
-#define SBR_FWD_CASE(G_, BT_) if (L.G == G_ && BT == BT_) rc = launch_tc(m, rnn_fwd_tc_kernel<G_, BT_>, p, n_tiles, a, FWD_NT);
-  rc = 1;
-  SBR_FWD_CASE(4, 16) SBR_FWD_CASE(4, 8) SBR_FWD_CASE(3, 16) SBR_FWD_CASE(3, 8) SBR_FWD_CASE(1, 16) SBR_FWD_CASE(1, 8)
+  // one launch = one tile height: tensor map with the matching box, tile order, stream
+  auto launch_one = [&](int bt, int n_tiles, const unsigned char* order, int use_order, cudaStream_t stream) -> int {
+    TcArgs v = a;
+    v.use_order = use_order;
+    if (order) memcpy(v.order, order, sizeof(v.order));
+    if (L.hT && B % bt == 0) { v.hT = L.hT; v.hT_part = L.hT_part; v.hT_tile = L.hT_tile; }
+    if (!make_map2d(&v.tm_xg, L.Xg, (uint64_t)m->T * m->B, (uint64_t)L.G * L.H, p.Hs, bt)) {
+      sbr_set_error(m, SBR_E_CUDA, "cuTensorMapEncodeTiled failed (Xg, H=%d Hs=%d BT=%d)", L.H, p.Hs, bt);
+      return SBR_E_CUDA;
+    }
+#define SBR_FWD_CASE(G_, BT_) if (L.G == G_ && bt == BT_) return launch_tc(m, rnn_fwd_tc_kernel<G_, BT_>, p, n_tiles, v, FWD_NT, stream);
+    SBR_FWD_CASE(4, 16) SBR_FWD_CASE(4, 8) SBR_FWD_CASE(3, 16) SBR_FWD_CASE(3, 8) SBR_FWD_CASE(1, 16) SBR_FWD_CASE(1, 8)
 #undef SBR_FWD_CASE
+    return 1;
+  };
+  if (sc.extra16 >= 0) {
+    // mixed tiling: the shortest 16-row group as ONE 16-row tile on the aux stream, concurrent with the 8-row tiles
+    unsigned char one[64] = {(unsigned char)sc.extra16};
+    CU_TRY(m, cudaEventRecord(m->ev_aux_fork, m->stream));
+    CU_TRY(m, cudaStreamWaitEvent(m->aux, m->ev_aux_fork, 0));
+    if ((rc = launch_one(16, 1, one, 1, m->aux))) return rc;
+    CU_TRY(m, cudaEventRecord(m->ev_aux_join, m->aux));
+  }
+  rc = launch_one(BT, sc.n_tiles, sc.order, sc.use_order, m->stream);
+  if (sc.extra16 >= 0 && rc == 0) CU_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_aux_join, 0));
   if (rc == 0 && a.dbg && L.G == 4) {
     static int calls = 0;
     if (++calls == 8) {
@@ -1300,22 +1335,8 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
   a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   const TileSched sc = schedule_tiles(m, p, B, t_max, 0.75f);   // bwd: 4118 vs 5477 cycles per step (8 vs 16 rows)
-  const int BT = sc.BT, n_tiles = sc.n_tiles;
-  p.smem = tc_bwd_smem(p, BT);
-  a.use_order = sc.use_order;
-  memcpy(a.order, sc.order, sizeof(a.order));
-  if (L.aT && B % BT == 0) { a.aT = L.aT; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile; }
+  const int BT = sc.BT;
   a.g_b = m->grads + L.b;
-  {
-    // tensor maps over the whole allocations ([T*Bmax (+Bmax)] rows): box = [BT x Hs]
-    const uint64_t TB = (uint64_t)m->T * m->B;
-    bool ok = true;
-    if (L.G > 1) ok = ok && make_map2d(&a.tm_act, L.act, TB, 4 * (uint64_t)L.H, p.Hs, BT);
-    if (L.G == 4) ok = ok && make_map2d(&a.tm_cs, L.cs, TB + m->B, L.H, p.Hs, BT);
-    ok = ok && make_map2d(&a.tm_hs, L.hs, TB + m->B, L.H, p.Hs, BT);
-    if (a.dhs) ok = ok && make_map2d(&a.tm_dhs, L.dhs, TB, L.H, p.Hs, BT);
-    if (!ok) { sbr_set_error(m, SBR_E_CUDA, "cuTensorMapEncodeTiled failed (H=%d Hs=%d BT=%d)", L.H, p.Hs, BT); return SBR_E_CUDA; }
-  }
   a.ld_p = 3;
   if (const char* e = getenv("SBR_TC_LDP")) a.ld_p = std::max(1, std::min(3, atoi(e)));
   if (const char* e = getenv("SBR_TC_EXPERIMENT")) a.xflags = atoi(e);
@@ -1334,12 +1355,39 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
               0.0, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n);
     }
   }
+  auto launch_one = [&](int bt, int n_tiles, const unsigned char* order, int use_order, cudaStream_t stream) -> int {
+    TcArgs v = a;
+    TcPlan q = p;
+    q.smem = tc_bwd_smem(p, bt);
+    v.use_order = use_order;
+    if (order) memcpy(v.order, order, sizeof(v.order));
+    if (L.aT && B % bt == 0) { v.aT = L.aT; v.aT_part = L.aT_part; v.aT_tile = L.aT_tile; }
+    // tensor maps over the whole allocations ([T*Bmax (+Bmax)] rows): box = [bt x Hs]
+    const uint64_t TB = (uint64_t)m->T * m->B;
+    bool ok = true;
+    if (L.G > 1) ok = ok && make_map2d(&v.tm_act, L.act, TB, 4 * (uint64_t)L.H, p.Hs, bt);
+    if (L.G == 4) ok = ok && make_map2d(&v.tm_cs, L.cs, TB + m->B, L.H, p.Hs, bt);
+    ok = ok && make_map2d(&v.tm_hs, L.hs, TB + m->B, L.H, p.Hs, bt);
+    if (v.dhs) ok = ok && make_map2d(&v.tm_dhs, L.dhs, TB, L.H, p.Hs, bt);
+    if (!ok) { sbr_set_error(m, SBR_E_CUDA, "cuTensorMapEncodeTiled failed (H=%d Hs=%d BT=%d)", L.H, p.Hs, bt); return SBR_E_CUDA; }
 #define SBR_BWD_CASE(G_, MT_) \
-  if (L.G == G_ && p.MT == MT_ && BT == 16) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 16>, p, n_tiles, a, bwd_threads(16)); \
-  if (L.G == G_ && p.MT == MT_ && BT == 8) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 8>, p, n_tiles, a, bwd_threads(8));
-  SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)
+    if (L.G == G_ && p.MT == MT_ && bt == 16) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 16>, q, n_tiles, v, bwd_threads(16), stream); \
+    if (L.G == G_ && p.MT == MT_ && bt == 8) return launch_tc(m, rnn_bwd_tc_kernel<G_, MT_, 8>, q, n_tiles, v, bwd_threads(8), stream);
+    SBR_BWD_CASE(4, 1) SBR_BWD_CASE(4, 2) SBR_BWD_CASE(3, 1) SBR_BWD_CASE(3, 2) SBR_BWD_CASE(1, 1) SBR_BWD_CASE(1, 2)
 #undef SBR_BWD_CASE
-  return 1;
+    return 1;
+  };
+  int rc = 0;
+  if (sc.extra16 >= 0) {
+    unsigned char one[64] = {(unsigned char)sc.extra16};
+    CU_TRY(m, cudaEventRecord(m->ev_aux_fork, m->stream));
+    CU_TRY(m, cudaStreamWaitEvent(m->aux, m->ev_aux_fork, 0));
+    if ((rc = launch_one(16, 1, one, 1, m->aux))) return rc;
+    CU_TRY(m, cudaEventRecord(m->ev_aux_join, m->aux));
+  }
+  rc = launch_one(BT, sc.n_tiles, sc.order, sc.use_order, m->stream);
+  if (sc.extra16 >= 0 && rc == 0) CU_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_aux_join, 0));
+  return rc;
 }
 
 int tc_scan_applies(int G, int H) {

@@ -107,6 +107,22 @@ def test_cce_gradients_tensor_core_wgrad(cell, H, B, rows, monkeypatch):
     check_grads(spec, B=B, T=11, seed=12)
 
 
+@pytest.mark.parametrize("cell,H,B", [("LSTM", 200, 128), ("GRU", 100, 64), ("Vanilla", 48, 32), ("LSTM", 64, 128)])
+def test_cce_gradients_mixed_tiling(cell, H, B, monkeypatch):
+    """Mixed tiling: the shortest 16-row group runs as one 16-row tile on a second stream next to the 8-row tiles
+    (what a batch of 128 rows does by default on the 15 co-resident cluster slots of a B200)."""
+    monkeypatch.setenv("SBR_TC_FORCE_MIXED", "1")
+    spec = O.Spec(n_items=211, cell=cell, layers=(H,), loss="CCE")
+    check_grads(spec, B=B, T=11, seed=5)
+
+
+def test_stacked_layers_8_row_tiles():
+    """Upper-layer gradient (dhs) streamed by TMA into 8-row tiles, and the mixed tiling on a stacked model."""
+    spec = O.Spec(n_items=150, cell="LSTM", layers=(32, 40), loss="CCE", regularization=-0.02)
+    check_grads(spec, B=16, T=8, seed=2)
+    check_grads(spec, B=128, T=6, seed=3)
+
+
 @pytest.mark.parametrize("cell,H", [("GRU", 100), ("LSTM", 200), ("Vanilla", 48), ("LSTM", 52)])
 def test_cce_gradients_8_row_tiles_ragged_batch(cell, H, monkeypatch):
     """8-row cluster tiles with a batch that is not a multiple of 8 (last tile partly empty)."""
