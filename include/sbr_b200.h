@@ -158,6 +158,12 @@ SBR_API const char* sbr_stage_name(int i);            /* "h2d","gather","rnn_fwd
 SBR_API int sbr_set_profiling(sbr_model* m, int on);  /* record a cudaEvent pair around every stage */
 SBR_API int sbr_stage_times(sbr_model* m, float ms[SBR_N_STAGES]);   /* of the last profiled step   */
 SBR_API int64_t sbr_kernel_launches(const sbr_model* m);             /* kernels launched since create */
+/* Host-only: how the tcgen05 scan launchers would tile a batch with these lengths on `slots` co-resident 8-CTA
+ * clusters (rnn_tc.cu::plan_tiles): tile height of the main launch (8 / 16 rows), its tiles in launch order (longest
+ * first, order64 has room for 64), and the 16-row group that runs as a second launch in the mixed tiling (-1: none).
+ * `lens` may be NULL (static rule).  Touches no device; used by the CPU tests. */
+SBR_API int sbr_plan_scan_tiles(const int32_t* lens, int B, int t_max, int slots, float ratio8,
+                                int* tile_rows, int* n_tiles, int* extra16, unsigned char* order64);
 /* device-side stopwatch on the handle's stream (cudaEvent pair): start synchronises the stream
  * first, stop blocks until the stop event has completed and returns the elapsed milliseconds */
 SBR_API int sbr_timer_start(sbr_model* m);

@@ -80,6 +80,8 @@ SIGNATURES = {
     "sbr_set_profiling": (C.c_int, [_P, C.c_int]),
     "sbr_stage_times": (C.c_int, [_P, _f32p]),
     "sbr_kernel_launches": (C.c_int64, [_P]),
+    "sbr_plan_scan_tiles": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int), C.POINTER(C.c_ubyte)]),
     "sbr_timer_start": (C.c_int, [_P]),
     "sbr_timer_stop": (C.c_int, [_P, _f32p]),
 }

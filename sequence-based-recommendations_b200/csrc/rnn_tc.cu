@@ -103,23 +103,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
                "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
                "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
-}
 __device__ __forceinline__ uint32_t map_to_rank(uint32_t cta_addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// asynchronous 16-byte store into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16)
-// when the data has landed (release at cluster scope) -- no fence, no barrier on the sender side
-__device__ __forceinline__ void st_async_v4(uint32_t addr, float4 v, uint32_t mbar_addr) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-               :: "r"(addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
-                  "r"(__float_as_uint(v.w)), "r"(mbar_addr) : "memory");
 }
 // bulk asynchronous copy of a contiguous block of THIS CTA's shared memory into a peer CTA's shared memory
 // (TMA engine, no per-thread stores); the peer's mbarrier receives complete_tx(bytes) when it has landed
@@ -1175,11 +1162,10 @@ int makespan(const int* t_end, int n, int slots) {   // t_end sorted descending
   }
   return *std::max_element(busy.begin(), busy.end());
 }
-TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, float ratio8) {
+// pure host planner (no CUDA calls): exported for the CPU tests as sbr_plan_scan_tiles
+TileSched plan_tiles(const int32_t* hl, int B, int t_max, int slots, float ratio8) {
   TileSched sc{};
   sc.extra16 = -1;
-  const int slots = resident_clusters(p);
-  const int32_t* hl = m->cur_hlen;
   auto tiles_of = [&](int BT, int* t_end, unsigned char* order) {
     const int n = cdiv(B, BT);
     std::vector<std::pair<int, int>> v(n);
@@ -1229,6 +1215,9 @@ TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, 
   sc.use_order = 1;
   memcpy(sc.order, BT == 8 ? o8 : o16, 64);
   return sc;
+}
+TileSched schedule_tiles(const sbr_model* m, const TcPlan& p, int B, int t_max, float ratio8) {
+  return plan_tiles(m->cur_hlen, B, t_max, resident_clusters(p), ratio8);
 }
 
 template <typename Kern>
@@ -1388,6 +1377,19 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   rc = launch_one(BT, sc.n_tiles, sc.order, sc.use_order, m->stream);
   if (sc.extra16 >= 0 && rc == 0) CU_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_aux_join, 0));
   return rc;
+}
+
+// Host-only view of the scan launch plan for a batch with the given lengths on `slots` co-resident cluster slots
+// (diagnostics / CPU tests; touches no device).  tile_rows = 8 or 16 for the main launch; order[0..n_tiles) = its
+// tiles in launch order (units of tile_rows rows); extra16 = the 16-row group of the second launch, or -1.
+extern "C" SBR_API int sbr_plan_scan_tiles(const int32_t* lens, int B, int t_max, int slots, float ratio8,
+                                           int* tile_rows, int* n_tiles, int* extra16, unsigned char* order64) {
+  if (B < 1 || slots < 1 || !tile_rows || !n_tiles || !extra16 || !order64) return SBR_E_ARG;
+  const TileSched sc = plan_tiles(lens, B, t_max, slots, ratio8);
+  *tile_rows = sc.BT; *n_tiles = sc.n_tiles; *extra16 = sc.extra16;
+  if (sc.use_order) memcpy(order64, sc.order, 64);
+  else for (int i = 0; i < 64; ++i) order64[i] = (unsigned char)i;
+  return 0;
 }
 
 int tc_scan_applies(int G, int H) {
