@@ -596,7 +596,6 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
   const int PB = C * TC_BT * Hs;                // floats per part / send buffer
   float* stag = sbuf + 2 * PB;                  // [4][7][BT][Hs] saved tensors of a step, filled by the loader warps
   const int SGB = 7 * TC_BT * Hs;
-  constexpr bool ldr = false;                   // (no loader warps: the TMA engine streams the saved tensors)
   __shared__ __align__(8) uint64_t sv_full[4];
   __shared__ __align__(8) uint64_t part_full[2];
   __shared__ __align__(8) uint64_t mma_done;
@@ -616,7 +615,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (!ldr) {
+  {
     for (int i = tid; i < 2 * Kb * TC_BT; i += FWD_NT) Bhi[i] = 0.f;            // Bhi and Blo are contiguous
     for (int i = tid; i < 4 * C * TC_BT * Hs; i += FWD_NT) part[i] = 0.f;          // part and sbuf are contiguous
   }
@@ -632,7 +631,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
 
   // ---- A operand tiles: row = hidden index k, column kk = 4*j + g  <->  W_hid[k][g*H + j0 + j]
   //      warps 0-3 stage the hi copies, warps 4-7 the lo copies
-  if (!ldr) {
+  {
     const bool want_lo = warp >= 4;
     for (int mt = 0; mt < MT; ++mt) {
       const int k = mt * 128 + quad * 32 + (tid & 31);
@@ -666,9 +665,9 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
 
   // thread <-> (row, unit) as in the forward kernel: with 8-row tiles a warp's 16-byte stores of da into the B
   // operand ([unit][row][4 gates]) are 512 contiguous bytes (conflict-free) instead of 32 hits on one bank group
-  const int eb = ldr ? 0 : ((BT == 8) ? (tid & 7) : tid / TPR);
+  const int eb = (BT == 8) ? (tid & 7) : tid / TPR;
   const int ju = (BT == 8) ? (warp * 4 + ((tid & 31) >> 3)) : NU * (tid % TPR);
-  const bool own = !ldr && ju < nj;
+  const bool own = ju < nj;
   const bool row_ok = b0 + eb < B;
   float carry[NU], dcs[NU], dpe[NU][3], wci[NU], wcf[NU], wco[NU];
   float dbias[NU][4];                                                   // sum over steps of dXg (bias gradient)
@@ -754,7 +753,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
   };
-  auto ldr_issue = [&](int t) {      // executed by ONE thread
+  auto sv_issue = [&](int t) {       // executed by ONE thread
     if (t < 0 || (a.xflags & 128)) return;
     float* sg = stag + (t & (LD_D - 1)) * SGB;
     uint64_t* bar = &sv_full[t & (LD_D - 1)];
@@ -786,7 +785,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
   };
   if (tid == FWD_NT - 32) {     // lane 0 of warp 7 (the one compute warp that never issues MMAs)
     asm volatile("prefetch.tensormap [%0];" :: "l"(&a.tm_act) : "memory");
-    for (int i = 1; i <= LD_P; ++i) ldr_issue(t_end - i);
+    for (int i = 1; i <= LD_P; ++i) sv_issue(t_end - i);
   }
 
   // one phase of part_full[x] = the partial dh blocks of my units have landed from the C-1 other CTAs
@@ -848,7 +847,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
     }
 
     // ---- phase A: dh_t = carry + partials of step t+1 (+ gradient from the layer above); gate gradients
-    if (t < t_end - 1 && !ldr) {
+    if (t < t_end - 1) {
       mbar_wait_cluster(&part_full[rpar], n_wait[rpar] & 1);
       n_wait[rpar]++;
       if (tid == 0) mbar_arrive_expect_tx(&part_full[rpar], tx_bytes);
@@ -935,14 +934,14 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
         for (int g = 0; g < 4; ++g) { dx_out[u][g] = dx[u][g]; dac_out[u] = da[u][2]; dbias[u][g] += dx[u][g]; }
     }
     TC_BSTAMP(2);
-    if (!ldr) PROXY_FENCE_SMEM();
+    PROXY_FENCE_SMEM();
     TC_BSTAMP(3);
     TC_FENCE_BEFORE();
     __syncthreads();
     TC_FENCE_AFTER();
     TC_BSTAMP(4);
     // stage (t - LD_P) % LD_D last held step t+1, which every thread read before the barrier above: refill it
-    if (tid == FWD_NT - 32) ldr_issue(t - LD_P);
+    if (tid == FWD_NT - 32) sv_issue(t - LD_P);
 
     // ---- phase B: partial dh_{t-1}[b][k] = sum_kk da[b][kk] * W_hid[k][kk], all k (MT tiles of 128 rows)
     if (warp >= 4 && warp <= 4 + MT) {
@@ -978,7 +977,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
       if (G == 3) stn<NU>(a.dac + row * H + j0 + ju, dac_out);
     }
     TC_BSTAMP(5);
-    if (!ldr) mbar_wait_cta(&mma_done, (t_end - 1 - t) & 1);
+    mbar_wait_cta(&mma_done, (t_end - 1 - t) & 1);
     TC_FENCE_AFTER();
     TC_BSTAMP(6);
     {
@@ -997,7 +996,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
     }
     // ---- phase C: reduce-scatter: one bulk copy of the [BT x Hs] block per peer, into slot [par][my rank]
     TC_BSTAMP(7);
-    if (!ldr) PROXY_FENCE_SMEM();
+    PROXY_FENCE_SMEM();
     TC_BSTAMP(8);
     TC_FENCE_BEFORE();
     __syncthreads();
@@ -1022,7 +1021,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
 #endif
 
   // ---- gradients of the learned initial states and of the peepholes
-  if (t_end > 0 && !ldr) {
+  if (t_end > 0) {
     mbar_wait_cluster(&part_full[0], n_wait[0] & 1);   // step t = 0 wrote buffer 0
   }
   if (own && row_ok) {
