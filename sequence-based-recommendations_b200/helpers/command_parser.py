@@ -65,6 +65,8 @@ _PREDICTOR_FLAGS = [
 _B200_FLAGS = [
     (('--device',), dict(help='CUDA ordinal of this rank (default: LOCAL_RANK or 0)', default=None, type=int)),
     (('--seed',), dict(help='Seed of the python / numpy RNGs that drive batch construction', default=None, type=int)),
+    (('--prefetch',), dict(help='Assemble this many mini-batches ahead in a background thread (the reference\'s '
+                                'disabled threaded_generator); 0 = off', default=0, type=int)),
 ]
 
 
@@ -96,7 +98,7 @@ def get_predictor(args, **dist):
                   updater=get_update_manager(args), target_selection=get_target_selection(args),
                   sequence_noise=get_sequence_noise(args), recurrent_layer=get_recurrent_layers(args),
                   use_ratings_features=args.rf, use_movies_features=args.mf, use_users_features=args.uf,
-                  batch_size=args.batch_size)
+                  batch_size=args.batch_size, prefetch_batches=getattr(args, 'prefetch', 0))
     common.update(dist)
     if args.loss == 'CCE':
         return RNNOneHot(diversity_bias=args.diversity_bias, regularization=args.regularization, **common)

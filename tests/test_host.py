@@ -184,3 +184,54 @@ def test_pareto_front(dataset):
     m = {"sps": [0.1, 0.3, 0.2], "recall": [0.3, 0.1, 0.2]}
     assert p.get_pareto_front(m, ["sps", "recall"]) == [0, 1, 2]
     assert p.get_pareto_front({"sps": [0.1, 0.3, 0.2]}, ["sps"]) == [1]
+
+
+# ---------------------------------------------------------------------------------------------
+# threaded_generator: the reference's (disabled) prefetch helper, rnn_base.py:34-56 / :273-274
+# ---------------------------------------------------------------------------------------------
+def test_threaded_generator_preserves_order_and_content():
+    from sbr_b200.neural_networks.rnn_base import threaded_generator
+    src = [(i, np.full(3, i)) for i in range(500)]
+    out = list(threaded_generator(iter(src), num_cached=7))
+    assert [i for i, _ in out] == list(range(500))
+    assert all((a == i).all() for i, a in out)
+    assert list(threaded_generator(iter([]), num_cached=3)) == []
+
+
+def test_threaded_generator_reraises_producer_errors_in_place():
+    from sbr_b200.neural_networks.rnn_base import threaded_generator
+
+    def gen():
+        yield 1
+        yield 2
+        raise KeyError("boom")
+
+    g = threaded_generator(gen(), num_cached=2)
+    assert next(g) == 1 and next(g) == 2
+    with pytest.raises(KeyError):
+        next(g)
+    with pytest.raises(StopIteration):
+        next(g)
+
+
+def test_threaded_generator_close_stops_an_endless_producer():
+    import itertools
+    import time as _time
+    from sbr_b200.neural_networks.rnn_base import threaded_generator
+    g = threaded_generator(itertools.count(), num_cached=4)
+    assert [next(g) for _ in range(10)] == list(range(10))
+    g.close()
+    _time.sleep(0.2)
+    assert not g._thread.is_alive()
+    with pytest.raises(StopIteration):
+        next(g)
+
+
+def test_prefetch_flag_reaches_the_predictor():
+    from sbr_b200.helpers import command_parser as cp
+    args = cp.command_parser(cp.predictor_command_parser, argv=["--prefetch", "16"])
+    assert args.prefetch == 16
+    p = cp.get_predictor(args)
+    assert p.prefetch_batches == 16
+    args = cp.command_parser(cp.predictor_command_parser, argv=[])
+    assert cp.get_predictor(args).prefetch_batches == 0
