@@ -394,13 +394,19 @@ class RNNBase(object):
                 else:
                     seq_lengths = [int(len(sequence) / 2)]
                 skipped_seq = 0
+                # the rows of one user are windows of the same sequence: encode it once, hand every row a view
+                # (4th element, consumed by _fill_inputs; the first three are the reference's [user, input, targets])
+                ids = self._features_of(sequence) if len(seq_lengths) > 1 else None
                 for l in seq_lengths:
                     target = self.target_selection(sequence[l:], test=test)
                     if len(target) == 0:
                         skipped_seq += 1
                         continue
                     start = max(0, l - self.max_length)
-                    sequences.append([user_id, sequence[start:l], target])
+                    row = [user_id, sequence[start:l], target]
+                    if ids is not None:
+                        row.append(ids[start:l])
+                    sequences.append(row)
                 j += len(seq_lengths) - skipped_seq
             if test:
                 yield self._prepare_input(sequences), [int(i[0]) for i in sequence[seq_lengths[0]:]]
@@ -412,13 +418,15 @@ class RNNBase(object):
         float32, plus the ragged list of seen item ids (the reference's dense `exclude` rows)."""
         B = len(sequences)
         X = np.zeros((B, self.max_length, self._input_size()), dtype=np.int32)
-        mask = np.zeros((B, self.max_length), dtype=np.float32)
+        lens = np.empty(B, dtype=np.int64)
         seen = []
-        for i, (user_id, in_seq, target) in enumerate(sequences):
+        for i, row in enumerate(sequences):
+            in_seq = row[1]
             n = len(in_seq)
-            X[i, :n, :] = self._features_of(in_seq)
-            mask[i, :n] = 1
+            X[i, :n, :] = row[3] if len(row) > 3 else self._features_of(in_seq)   # pre-encoded view, see _gen_mini_batch
+            lens[i] = n
             seen.append(X[i, :n, 0])
+        mask = (np.arange(self.max_length)[None, :] < lens[:, None]).astype(np.float32)
         return X, mask, seen
 
     def _print_progress(self, iterations, epochs, start_time, train_costs, metrics, validation_metrics):

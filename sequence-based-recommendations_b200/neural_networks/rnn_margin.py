@@ -56,7 +56,8 @@ class RNNMargin(rnn.RNNBase):
         off = np.zeros(B + 1, dtype=np.int32)
         ids = []
         w = np.zeros(B, dtype=np.float32)
-        for i, (user_id, in_seq, target) in enumerate(sequences):
+        for i, row in enumerate(sequences):
+            in_seq, target = row[1], row[2]       # rows may carry a 4th element (pre-encoded ids, rnn_base._gen_mini_batch)
             t = np.asarray(target)[:, 0].astype(np.int32)
             ids.append(t)
             off[i + 1] = off[i] + len(t)

@@ -235,3 +235,35 @@ def test_prefetch_flag_reaches_the_predictor():
     assert p.prefetch_batches == 16
     args = cp.command_parser(cp.predictor_command_parser, argv=[])
     assert cp.get_predictor(args).prefetch_batches == 0
+
+
+@pytest.mark.parametrize("rf", [False, True])
+def test_pre_encoded_rows_give_the_same_batches(rf, tmp_path):
+    """_gen_mini_batch encodes a user's sequence once and hands the rows views of it; the padded tensors must be
+    identical to encoding every row on its own (the reference's per-row loop, rnn_one_hot.py:90-101)."""
+    from sbr_b200.neural_networks.rnn_one_hot import RNNOneHot
+    from sbr_b200.neural_networks.rnn_margin import RNNMargin
+    from sbr_b200.neural_networks.target_selection import SelectTargets
+    d = str(tmp_path / "ds") + "/"
+    synthetic.write_dataset(d, n_users=60, n_items=80, min_len=8, max_len=40, seed=3)
+    ds = DataHandler(d)
+    for cls, kw in ((RNNOneHot, {}), (RNNMargin, dict(target_selection=SelectTargets(n_targets=2)))):
+        p = cls(max_length=12, batch_size=16, use_ratings_features=rf, use_movies_features=False,
+                use_users_features=False, **kw)
+        p.n_items = ds.n_items
+        p.set_dataset(ds)
+        captured = []
+        orig = p._prepare_input
+        p._prepare_input = lambda seqs: (captured.append([r[:3] for r in seqs]), orig(seqs))[1]
+        random.seed(4); np.random.seed(4)
+        gen = p._gen_mini_batch(ds.training_set())
+        for _ in range(5):
+            out = next(gen)
+            ref = orig(captured[-1])            # same rows without the pre-encoded 4th element
+            assert any(len(r) > 3 for r in captured[-1]) is False
+            np.testing.assert_array_equal(out[0], ref[0])
+            np.testing.assert_array_equal(out[1], ref[1])
+            assert all((a == b).all() for a, b in zip(out[-1], ref[-1]))
+            assert out[0].dtype == np.int32 and out[1].dtype == np.float32
+            lens = out[1].sum(1).astype(int)
+            assert ((out[1] == 1) == (np.arange(12)[None, :] < lens[:, None])).all()
