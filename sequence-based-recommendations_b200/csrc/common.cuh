@@ -162,6 +162,7 @@ struct sbr_model {
   // profiling
   bool profiling = false;
   bool skip_update = false;
+  bool grads_dirty = false;            // the arena holds gradients of an inspection step (skip_update just went 1 -> 0)
   cudaEvent_t ev[SBR_N_STAGES + 1] = {};
   cudaEvent_t timer[2] = {};
   float stage_ms[SBR_N_STAGES] = {};

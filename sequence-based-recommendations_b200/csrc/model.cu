@@ -470,6 +470,9 @@ extern "C" int sbr_reset_optimizer(sbr_model* m) {
 
 extern "C" int sbr_set_skip_update(sbr_model* m, int flag) {
   if (!m) return SBR_E_ARG;
+  // gradients of inspection steps stay in the arena (the optimizer kernel is what re-zeroes it): the next real step
+  // must not accumulate on top of them
+  if (m->skip_update && !flag) m->grads_dirty = true;
   m->skip_update = flag != 0;
   return 0;
 }
@@ -719,9 +722,10 @@ static int launch_deferred_output_grads(sbr_model* m) {
 
 static int begin_step(sbr_model* m) {
   CU_TRY(m, cudaSetDevice(m->dev));
-  if (m->skip_update)  // gradients of the previous (inspection) step are still in the arena
+  if (m->skip_update || m->grads_dirty) {  // gradients of the previous (inspection) step are still in the arena
     CU_TRY(m, cudaMemsetAsync(m->grads, 0, ((size_t)m->P_pad + 4) * sizeof(float), m->stream));
-  else
+    m->grads_dirty = false;
+  } else
     CU_TRY(m, cudaMemsetAsync(m->grads + m->cost_slot, 0, 4 * sizeof(float), m->stream));
   return 0;
 }

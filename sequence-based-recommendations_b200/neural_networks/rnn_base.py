@@ -47,8 +47,10 @@ class threaded_generator(object):
     Iteration order and content are exactly those of `generator`.  An exception raised by the producer is re-raised
     in the consumer at the position where it happened; `close()` (also called when the consumer is garbage
     collected) stops the producer.  The producer and the consumer share the global `random` / `numpy.random`
-    state: do not draw from them in the consumer while the producer runs if a seeded run must be reproducible
-    (the train loop does not; the periodic validation only consumes validation data)."""
+    state, so the consumer must not draw from them while the producer runs if a seeded run (or a multi-rank run,
+    where every rank has to build the same global batches) is to stay reproducible.  The train loop does not; the
+    periodic validation does not either: test batches of RNNSampling carry a constant sample vector (the test
+    function ignores it) instead of fresh draws, and `--rand_test_target` is refused together with prefetching."""
 
     _END = object()
 
@@ -104,7 +106,7 @@ class RNNBase(object):
     def __init__(self, sequence_noise=None, recurrent_layer=None, updater=None, target_selection=None,
                  interactions_are_unique=True, other_features=None, use_ratings_features=True, movies_features=None,
                  use_movies_features=True, users_features=None, use_users_features=True, max_length=MAX_LENGTH,
-                 batch_size=BATCH_SIZE, device=0, n_ranks=1, rank=0, nccl_id=None, prefetch_batches=0):
+                 batch_size=BATCH_SIZE, device=0, n_ranks=1, rank=0, nccl_id=None, prefetch_batches=0, init_seed=None, control=None):
         self.sequence_noise = sequence_noise if sequence_noise is not None else SequenceNoise()
         self.recurrent_layer = recurrent_layer if recurrent_layer is not None else RecurrentLayers()
         self.updater = updater if updater is not None else Adagrad()
@@ -117,6 +119,12 @@ class RNNBase(object):
         self.batch_size = batch_size
         self.device, self.n_ranks, self.rank, self.nccl_id = device, n_ranks, rank, nccl_id
         self.prefetch_batches = int(prefetch_batches)   # > 0: assemble mini-batches in a background thread
+        # seed of the parameter initialisation.  The reference draws from the (unseeded) global numpy RNG through
+        # lasagne.random.get_rng(); data-parallel replicas must start identical, so with several ranks the default
+        # is a fixed seed, with one rank the global numpy RNG like the reference.
+        self.init_seed = init_seed
+        # multi-rank control plane (helpers/rendezvous.Control) or None; used to make wall-clock decisions collective
+        self.control = control
         if batch_size % n_ranks != 0:
             raise ValueError("batch_size (%d) must be a multiple of the number of ranks (%d)" % (batch_size, n_ranks))
         self.local_batch = batch_size // n_ranks
@@ -151,6 +159,34 @@ class RNNBase(object):
         kw.update(self.updater.engine_kwargs())
         kw.update(self._engine_extra_kwargs())
         self.engine = _capi.Engine(**kw)
+        self._init_parameters()
+
+    last_layer_init = 1.0   # GlorotUniform gain of the output layer (RNNSampling overrides it, rnn_sampling.py:131)
+
+    def _init_parameters(self):
+        """Lasagne's initialisers for a freshly built network, in add_param order (the library allocates the
+        parameter arena zeroed): Gate W_in / W_hid / W_cell ~ Normal(std 0.1), b = 0 (lasagne Gate defaults used at
+        sparse_lstm.py:156-159,590-593,960-961); learned cell_init / hid_init = 0; EmbeddingLayer.W ~ Normal(std
+        0.01) (recurrent_layers.py:47); Dense / Blackout W ~ GlorotUniform(gain) (rnn_one_hot.py:65,
+        rnn_sampling.py:131, rnn_margin.py:103), b = 0."""
+        if self.init_seed is None:
+            rng = np.random.RandomState(20160901) if self.n_ranks > 1 else np.random
+        else:
+            rng = np.random.RandomState(self.init_seed)
+        vals = []
+        for name, shape in self.engine.param_infos():
+            leaf = name.split(".")[1]
+            if name == "emb.W":
+                v = rng.normal(0.0, 0.01, size=shape)
+            elif name == "out.W":
+                a = float(self.last_layer_init) * np.sqrt(6.0 / (shape[0] + shape[1]))
+                v = rng.uniform(-a, a, size=shape)
+            elif leaf.startswith("W_"):
+                v = rng.normal(0.0, 0.1, size=shape)
+            else:
+                v = np.zeros(shape)
+            vals.append(np.asarray(v, dtype=np.float32))
+        self.engine.set_all_param_values(vals)
 
     def _common_filename(self, epochs):
         """Common part of the checkpoint filename across sub classes (rnn_base.py:111-130)."""
@@ -281,6 +317,9 @@ class RNNBase(object):
             epochs_offset = self.load_last(save_dir)
 
         batch_generator = self._gen_mini_batch(self.sequence_noise(dataset.training_set()))
+        if self.prefetch_batches > 0 and not getattr(self.target_selection, 'determinist_test', True):
+            raise ValueError("--prefetch and --rand_test_target draw from the same RNG streams in two threads; "
+                             "use one or the other")
         if self.prefetch_batches > 0:       # the call the reference keeps commented out (rnn_base.py:273-274)
             batch_generator = threaded_generator(batch_generator, num_cached=self.prefetch_batches)
         start_time = time()
@@ -289,8 +328,23 @@ class RNNBase(object):
         metrics = {name: [] for name in self.metrics.keys()}
         filename = {}
         first_metric = list(self.metrics.keys())[0]
+        # Every rank must execute the same number of train steps (each one ends in a collective all-reduce) and take the
+        # same validate / stop decisions.  Decisions that depend on a wall clock are therefore taken on rank 0's clock:
+        # it is broadcast once per iteration, and only when such a decision exists (--max_time, --time_based_progress).
+        clock_matters = self.n_ranks > 1 and (time_based_progress or np.isfinite(max_time))
+        if clock_matters and self.control is None:
+            raise ValueError("max_time / time_based_progress with several ranks need the control plane "
+                             "(helpers/rendezvous.Control) so that all ranks stop on the same iteration")
+
+        def elapsed():
+            e = time() - start_time
+            return self.control.broadcast(e) if clock_matters else e
+
         try:
-            while time() - start_time < max_time and iterations < max_iter:
+            while iterations < max_iter:
+                now = elapsed()
+                if not now < max_time:
+                    break
                 try:
                     batch = next(batch_generator)
                     cost = self.train_function(*batch)
@@ -300,7 +354,7 @@ class RNNBase(object):
                     break
                 current_train_cost.append(cost)
                 iterations += 1
-                progress_indicator = int(time() - start_time) if time_based_progress else iterations
+                progress_indicator = int(elapsed()) if time_based_progress else iterations
                 if progress_indicator >= next_save:
                     if progress_indicator >= min_iterations:
                         epochs.append(epochs_offset + dataset.training_set.epochs)
@@ -409,7 +463,12 @@ class RNNBase(object):
                     sequences.append(row)
                 j += len(seq_lengths) - skipped_seq
             if test:
-                yield self._prepare_input(sequences), [int(i[0]) for i in sequence[seq_lengths[0]:]]
+                self._assembling_test_batch = True      # validation must not draw from the training RNG streams
+                try:
+                    batch_input = self._prepare_input(sequences)
+                finally:
+                    self._assembling_test_batch = False
+                yield batch_input, [int(i[0]) for i in sequence[seq_lengths[0]:]]
             else:
                 yield self._prepare_input(sequences)
 

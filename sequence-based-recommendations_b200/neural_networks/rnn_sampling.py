@@ -66,7 +66,11 @@ class RNNSampling(rnn.RNNBase):
         X, mask, seen = self._fill_inputs(sequences)
         Y = np.array([int(t[2][0][0]) for t in sequences], dtype=np.int32)
         pop = np.power(self.dataset.item_popularity[Y], self.diversity_bias).astype(np.float32)
-        if self.sampling_bias > 0:
+        if getattr(self, '_assembling_test_batch', False):
+            # validation / test batches: the test function never reads the samples (rnn_sampling.py:140-157); no draw,
+            # so that validation leaves the training RNG streams untouched
+            samples = np.zeros(self.effective_sampling, dtype=np.int32)
+        elif self.sampling_bias > 0:
             samples = np.array([self._popularity_sample() for _ in range(self.effective_sampling)], dtype=np.int32)
         else:
             samples = np.random.choice(self.n_items, self.effective_sampling).astype(np.int32)

@@ -51,12 +51,11 @@ def distributed_placement(args):
     device = args.device if args.device is not None else int(os.environ.get('LOCAL_RANK', '0'))
     if world == 1:
         return dict(device=device), None
-    import torch.distributed as dist
     from sbr_b200 import _capi
-    dist.init_process_group(backend='gloo')       # control plane; the data path is the library's NCCL all-reduce
-    box = [_capi.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
-    return dict(device=device, n_ranks=world, rank=rank, nccl_id=box[0]), dist
+    from sbr_b200.helpers.rendezvous import Control
+    ctl = Control()       # control plane (a TCP star next to MASTER_PORT); the data path is the library's NCCL all-reduce
+    nccl_id = ctl.broadcast(_capi.nccl_unique_id() if rank == 0 else None)
+    return dict(device=device, n_ranks=world, rank=rank, nccl_id=nccl_id, control=ctl), ctl
 
 
 def main(argv=None):
@@ -78,7 +77,7 @@ def main(argv=None):
                              validation_metrics=args.metrics.split(','))
     if dist is not None:
         dist.barrier()
-        dist.destroy_process_group()
+        dist.close()
     return result
 
 
