@@ -164,6 +164,14 @@ SBR_API int64_t sbr_kernel_launches(const sbr_model* m);             /* kernels 
  * `lens` may be NULL (static rule).  Touches no device; used by the CPU tests. */
 SBR_API int sbr_plan_scan_tiles(const int32_t* lens, int B, int t_max, int slots, float ratio8,
                                 int* tile_rows, int* n_tiles, int* extra16, unsigned char* order64);
+/* Diagnostics: C[M,N] = alpha * op(A) * op(B) (+ bias[n]) (+ beta * C) on the device the handle lives on, host buffers
+ * in and out (row-major; ta: A stored [K,lda]; tb: B stored [N,ldb]; beta in {0,1}; bias may be NULL).  engine 0 = the
+ * fp32 FFMA kernels (gemm.cu), 1 = the tcgen05 3xTF32 kernel (tc_gemm.cu), which is what every GEMM-shaped stage of
+ * the path runs on.  Used by the GPU tests to check the tensor-core kernel against float64 in isolation; `ms` (may be
+ * NULL) receives the device time of `reps` back-to-back launches. */
+SBR_API int sbr_debug_gemm(sbr_model* m, int engine, int ta, int tb, int M, int N, int K, const float* A, int lda,
+                           const float* B, int ldb, float* C, int ldc, float alpha, float beta, const float* bias,
+                           int reps, float* ms);
 /* device-side stopwatch on the handle's stream (cudaEvent pair): start synchronises the stream
  * first, stop blocks until the stop event has completed and returns the elapsed milliseconds */
 SBR_API int sbr_timer_start(sbr_model* m);

@@ -82,6 +82,8 @@ SIGNATURES = {
     "sbr_kernel_launches": (C.c_int64, [_P]),
     "sbr_plan_scan_tiles": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_ubyte)]),
+    "sbr_debug_gemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _f32p, C.c_int,
+                                 _f32p, C.c_int, C.c_float, C.c_float, _f32p, C.c_int, _f32p]),
     "sbr_timer_start": (C.c_int, [_P]),
     "sbr_timer_stop": (C.c_int, [_P, _f32p]),
 }
@@ -346,6 +348,23 @@ class Engine(object):
 
     def kernel_launches(self):
         return int(self.lib.sbr_kernel_launches(self._h))
+
+    def debug_gemm(self, A, B, ta=False, tb=False, C0=None, alpha=1.0, beta=0.0, bias=None, engine=1, reps=1):
+        """op(A) @ op(B) through one of the library's GEMM kernels (diagnostics / tests); returns (C, ms)."""
+        A, B = _f32(A), _f32(B)
+        M, K = (A.shape[1], A.shape[0]) if ta else A.shape
+        N = B.shape[0] if tb else B.shape[1]
+        assert (B.shape[1] if tb else B.shape[0]) == K
+        Cm = np.zeros((M, N), dtype=np.float32) if C0 is None else _f32(C0).copy()
+        bp = None if bias is None else _ptr(_f32(bias), _f32p)
+        bias_keep = None if bias is None else _f32(bias)
+        if bias_keep is not None:
+            bp = _ptr(bias_keep, _f32p)
+        ms = C.c_float(0)
+        self._check(self.lib.sbr_debug_gemm(self._h, int(engine), int(ta), int(tb), M, N, K, _ptr(A, _f32p), A.shape[1],
+                                            _ptr(B, _f32p), B.shape[1], _ptr(Cm, _f32p), N, float(alpha), float(beta), bp,
+                                            int(reps), C.byref(ms)))
+        return Cm, float(ms.value)
 
     def timer_start(self):
         self._check(self.lib.sbr_timer_start(self._h))

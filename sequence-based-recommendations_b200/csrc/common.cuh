@@ -156,6 +156,15 @@ struct sbr_model {
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
 
+  // per-step tensor-core scans (tc_gemm.cu): carried gradient state of the BPTT steps
+  float* step_carry = nullptr;   // [B, maxH]
+  float* step_dcs = nullptr;     // [B, maxH]
+  float* step_dpe = nullptr;     // [3][B, maxH]
+  // switches read once from the environment at sbr_create (diagnostics / A-B tests)
+  bool use_tc_gemm = true;       // SBR_DISABLE_TC_GEMM: FFMA GEMMs everywhere
+  bool use_step_scan = true;
+  bool no_side_stream = false, no_early_cost = false, disable_tc = false, disable_tc_bwd = false;   // SBR_NO_SIDE_STREAM, SBR_NO_EARLY_COST, SBR_DISABLE_TC, SBR_DISABLE_TC_BWD     // SBR_DISABLE_STEP_SCAN: FFMA cluster scans for hidden sizes beyond the tcgen05 cluster kernels
+
   // nccl
   void* nccl_comm = nullptr;
 
@@ -198,9 +207,20 @@ int tc_scan_applies(int G, int H);   // 1 when both tcgen05 scans handle this la
 // wgrad_tc.cu : dW_hid[H, G*H] += sum_rows h_prev[row]^T da[row] on tcgen05 (3xTF32) from the K-major copies
 int launch_wgrad_tc(sbr_model* m, const LayerDesc& L, int rows, float* dW, int ldw);
 
+// tc_gemm.cu : the same product on tcgen05 (3xTF32, operands split on the fly); returns 1 when it does not apply
+int launch_gemm_tc(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                   float* C, int ldc, float alpha, float beta, const float* bias);
+// per-step tensor-core scans for hidden sizes the cluster-resident kernels do not hold
+int step_scan_applies(const sbr_model* m, int G, int H);
+int launch_rnn_forward_steps(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last);
+int launch_rnn_backward_steps(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last);
+
 // gemm.cu : C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (row-major, beta in {0,1})
 int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
                 int ldb, float* C, int ldc, float alpha, float beta);
+// C = A * op(B) + bias[n] broadcast over the rows (input GEMMs: Xg = in W_in + b)
+int launch_gemm_bias(sbr_model* m, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                     float* C, int ldc, const float* bias);
 
 // loss.cu
 int launch_cce(sbr_model* m, float* logits, int ld, const float* bias, const int32_t* Y, const float* pop, int B,

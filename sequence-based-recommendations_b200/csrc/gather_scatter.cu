@@ -9,9 +9,9 @@
 // Both are HBM-bound row copies.  Rows are G*H floats (0.6-8 KB) so one warp moves one row with
 // 128-bit accesses; the grid is a multiple of the SM count.  The scatter is duplicate-heavy: a
 // reference mini-batch is B nested prefixes of ONE user's sequence (rnn_base.py:396-415), so at a
-// given timestep up to B rows carry the same item id.  The warp therefore groups its 32
-// consecutive (t, b) entries by id with match.any and issues ONE red.global.add per distinct id
-// (warp-aggregated atomics) instead of 32.
+// given timestep up to B rows carry the same item id.  A warp therefore owns 32 consecutive time-major
+// (t, b) rows x 128 columns, sums runs of equal ids in registers (run-length merge with warp shuffles)
+// and issues ONE 16-byte red.global.add.v4.f32 per run (warp-aggregated atomics) instead of one per row.
 #include "common.cuh"
 
 namespace {

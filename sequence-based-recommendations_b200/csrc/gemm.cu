@@ -325,6 +325,10 @@ int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float
     sbr_set_error(m, SBR_E_ARG, "gemm: beta must be 0 or 1");
     return SBR_E_ARG;
   }
+  {
+    const int rc = launch_gemm_tc(m, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, nullptr);   // tcgen05 3xTF32
+    if (rc <= 0) return rc;
+  }
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   int splits = 1;
   if (K > 0) {
@@ -349,20 +353,20 @@ int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float
     static const bool use_ffma = getenv("SBR_GEMM_FFMA") != nullptr;
     if (!use_ffma) {
       const size_t smem = (size_t)2 * MM_STAGES * MM_BK * MM_PITCH * sizeof(float);
-      static bool attr_set = false;
-      if (!attr_set) {
+      static std::vector<int> attr_devs;      // per-device attribute
+      if (std::find(attr_devs.begin(), attr_devs.end(), m->dev) == attr_devs.end()) {
         cudaFuncSetAttribute(sgemm_tn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        attr_devs.push_back(m->dev);
       }
       sgemm_tn_mma_kernel<<<grid, 256, smem, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
       KERNEL_CHECK(m);
       return 0;
     }
     const size_t smem = (size_t)TN_STAGES * TN_BK * (BM + BN) * sizeof(float);
-    static bool attr_set2 = false;
-    if (!attr_set2) {
+    static std::vector<int> attr_devs2;
+    if (std::find(attr_devs2.begin(), attr_devs2.end(), m->dev) == attr_devs2.end()) {
       cudaFuncSetAttribute(sgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set2 = true;
+      attr_devs2.push_back(m->dev);
     }
     sgemm_tn_kernel<<<grid, 256, smem, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
     KERNEL_CHECK(m);
@@ -374,4 +378,22 @@ int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float
   else sgemm_kernel<true, true><<<grid, 256, 0, m->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, kps, accumulate);
   KERNEL_CHECK(m);
   return 0;
+}
+
+__global__ void bias_rows_fill_kernel(float* __restrict__ out, const float* __restrict__ bias, int64_t rows, int cols, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  out[(i / cols) * ld + (i % cols)] = bias[i % cols];
+}
+
+int launch_gemm_bias(sbr_model* m, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                     float* C, int ldc, const float* bias) {
+  if (M <= 0 || N <= 0) return 0;
+  {
+    const int rc = launch_gemm_tc(m, false, tb, M, N, K, A, lda, B, ldb, C, ldc, 1.f, 0.f, bias);   // bias fused in the epilogue
+    if (rc <= 0) return rc;
+  }
+  bias_rows_fill_kernel<<<cdiv((int64_t)M * N, 256), 256, 0, m->stream>>>(C, bias, M, N, ldc);
+  KERNEL_CHECK(m);
+  return launch_gemm(m, false, tb, M, N, K, A, lda, B, ldb, C, ldc, 1.f, 1.f);
 }

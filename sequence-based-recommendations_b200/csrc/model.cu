@@ -220,7 +220,7 @@ extern "C" void sbr_destroy(sbr_model* m) {
   F(m->params); F(m->grads); F(m->opt_a); F(m->opt_b);
   for (LayerDesc& L : m->layers) { F(L.Xg); F(L.act); F(L.hs); F(L.cs); F(L.dXg); F(L.dac); F(L.dhs); F(L.hT); F(L.aT); }
   for (BatchSlot& s : m->slots) { F(s.X); F(s.len); F(s.Y); F(s.pop); }
-  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT);
+  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe);
   F(m->mY); F(m->mW); F(m->cells); F(m->Wc); F(m->dWc); F(m->bc);
   F(m->tgt_off); F(m->tgt_ids); F(m->w_neg); F(m->def_tgt); F(m->excl_off); F(m->excl_ids); F(m->topk_ids);
   if (m->h_len) cudaFreeHost(m->h_len);
@@ -250,6 +250,12 @@ static int create_impl(sbr_model* m) {
     return SBR_E_NOGPU;
   }
   m->n_sm = prop.multiProcessorCount;
+  m->use_tc_gemm = getenv("SBR_DISABLE_TC_GEMM") == nullptr;
+  m->use_step_scan = getenv("SBR_DISABLE_STEP_SCAN") == nullptr;
+  m->no_side_stream = getenv("SBR_NO_SIDE_STREAM") != nullptr;
+  m->no_early_cost = getenv("SBR_NO_EARLY_COST") != nullptr;
+  m->disable_tc = getenv("SBR_DISABLE_TC") != nullptr;
+  m->disable_tc_bwd = getenv("SBR_DISABLE_TC_BWD") != nullptr;
   {
     // the critical path (scans) outranks the side stream: when both have CTAs pending, the 8-CTA clusters of a scan
     // must not queue behind the output-layer weight-gradient GEMM
@@ -291,7 +297,7 @@ static int create_impl(sbr_model* m) {
     if (L.G == 3 && (rc = dev_alloc(m, &L.dac, TB * H))) return rc;
     if (li + 1 < m->layers.size() && (rc = dev_alloc(m, &L.dhs, TB * H))) return rc;
     // K-major pre-split copies for the tensor-core weight-gradient GEMM (only where the tcgen05 scans run)
-    if (tc_scan_applies(L.G, L.H) && m->B % 16 == 0 && !getenv("SBR_DISABLE_TC") && !getenv("SBR_DISABLE_TC_WGRAD")) {
+    if (tc_scan_applies(L.G, L.H) && m->B % 16 == 0 && !m->disable_tc && !getenv("SBR_DISABLE_TC_WGRAD")) {
       const size_t rq_h = (TB + B) / 4, rq_a = TB / 4;
       const size_t mts = (H + 127) / 128, nts = (GH + 127) / 128;
       L.hT_tile = (int64_t)rq_h * 512; L.hT_part = (int64_t)mts * L.hT_tile;
@@ -301,6 +307,15 @@ static int create_impl(sbr_model* m) {
     }
   }
   if ((rc = dev_alloc(m, &m->WhidT, (size_t)maxHGH))) return rc;
+  {
+    int maxH = 0;
+    for (const LayerDesc& L : m->layers) if (step_scan_applies(m, L.G, L.H) && !tc_scan_applies(L.G, L.H)) maxH = std::max(maxH, L.H);
+    if (maxH > 0) {
+      if ((rc = dev_alloc(m, &m->step_carry, B * maxH))) return rc;
+      if ((rc = dev_alloc(m, &m->step_dcs, B * maxH))) return rc;
+      if ((rc = dev_alloc(m, &m->step_dpe, 3 * B * maxH))) return rc;
+    }
+  }
   if (m->E > 0) {
     if ((rc = dev_alloc(m, &m->emb_out, TB * m->K * m->E))) return rc;
     if ((rc = dev_alloc(m, &m->demb, TB * m->K * m->E))) return rc;
@@ -598,8 +613,7 @@ static int forward_stack(sbr_model* m, const BatchSlot& s) {
         in = m->layers[li - 1].hs + (int64_t)B * m->layers[li - 1].H;   // skip the init row block
         I = m->layers[li - 1].H;
       }
-      if ((rc = bias_rows(m, L.Xg, m->params + L.b, rows, GH))) return rc;
-      if ((rc = launch_gemm(m, false, false, (int)rows, GH, I, in, I, m->params + L.W_in, GH, L.Xg, GH, 1.f, 1.f))) return rc;
+      if ((rc = launch_gemm_bias(m, false, (int)rows, GH, I, in, I, m->params + L.W_in, GH, L.Xg, GH, m->params + L.b))) return rc;
       if (li == 0) stage_mark(m, 2);
     }
     float* h_last = (li == m->L - 1) ? m->h_last : nullptr;
@@ -637,7 +651,7 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
     }
     // dW_hid = sum_t h_{t-1}^T da_t  : one tall-K GEMM outside the scan -- on tcgen05 from the K-major copies the
     // tc scans wrote, else the generic fp32 GEMM
-    const bool tc_wgrad = L.hT && L.aT && B % 16 == 0 && rows % 8 == 0 && rows > 0 && !getenv("SBR_DISABLE_TC_BWD");
+    const bool tc_wgrad = L.hT && L.aT && B % 16 == 0 && rows % 8 == 0 && rows > 0 && !m->disable_tc_bwd;
     if (tc_wgrad) {
       if ((rc = launch_wgrad_tc(m, L, rows, m->grads + L.W_hid, GH))) return rc;
     } else if (L.G == 3) {
@@ -647,7 +661,7 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
       if ((rc = launch_gemm(m, true, false, H, GH, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
     }
     // db = sum dXg: the tcgen05 BPTT kernel accumulates it itself; the FFMA fallback needs the column sum
-    if (!(tc_scan_applies(L.G, L.H) && !getenv("SBR_DISABLE_TC") && !getenv("SBR_DISABLE_TC_BWD")))
+    if (!(tc_scan_applies(L.G, L.H) && !m->disable_tc && !m->disable_tc_bwd))
       if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
     if (li == 0) stage_mark(m, 6);
     if (!gather_layer) {
@@ -669,14 +683,14 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
 // while the BPTT scan runs on 64 of the 148 SMs; the scatter while the weight-gradient GEMM runs) is
 // launched on m->side between side_fork() and side_join(); the two streams write disjoint gradient blocks.
 static int side_fork(sbr_model* m) {
-  if (getenv("SBR_NO_SIDE_STREAM")) return 0;   // diagnostics: everything on one stream
+  if (m->no_side_stream) return 0;   // diagnostics: everything on one stream
   CU_TRY(m, cudaEventRecord(m->ev_fork, m->stream));
   CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
   std::swap(m->stream, m->side);     // launchers use m->stream
   return 0;
 }
 static int side_return(sbr_model* m) {   // back to the main stream; the side work keeps running
-  if (getenv("SBR_NO_SIDE_STREAM")) return 0;
+  if (m->no_side_stream) return 0;
   std::swap(m->stream, m->side);
   return 0;
 }
@@ -696,7 +710,7 @@ static int output_backward_full(sbr_model* m, int B) {
   // is here (they only need the logit gradients and h_last), but the launches are issued AFTER the BPTT scan has
   // been launched on the main stream (launch_deferred_output_grads): a GEMM that reaches the SMs first would keep
   // some of the scan's 8-CTA clusters waiting for free SMs.
-  if (!getenv("SBR_NO_SIDE_STREAM")) CU_TRY(m, cudaEventRecord(m->ev_fork, m->stream));
+  if (!m->no_side_stream) CU_TRY(m, cudaEventRecord(m->ev_fork, m->stream));
   m->deferred_out_B = B;
   return 0;
 }
@@ -706,7 +720,7 @@ static int launch_deferred_output_grads(sbr_model* m) {
   if (B <= 0) return 0;
   m->deferred_out_B = 0;
   const int N = m->N, H = m->H_last;
-  const bool side = !getenv("SBR_NO_SIDE_STREAM");
+  const bool side = !m->no_side_stream;
   if (side) {
     CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
     std::swap(m->stream, m->side);
@@ -783,7 +797,7 @@ static int step_cce(sbr_model* m, const BatchSlot& s, float* cost) {
     if ((rc = launch_bias_reg(m, m->params + m->out_b, m->grads + m->out_b, N, m->cfg.regularization / (float)m->cfg.n_ranks,
                               m->grads + m->cost_slot))) return rc;
   // single rank: the cost is final here (no all-reduce): start its way to the host now, before the backward pass
-  if (cost && !m->nccl_comm && !m->profiling && !getenv("SBR_NO_EARLY_COST")) {
+  if (cost && !m->nccl_comm && !m->profiling && !m->no_early_cost) {
     CU_TRY(m, cudaMemcpyAsync(m->h_cost, m->grads + m->cost_slot, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(m, cudaEventRecord(m->ev_cost, m->stream));
     m->cost_early = true;
@@ -1007,6 +1021,47 @@ extern "C" int sbr_stage_times(sbr_model* m, float ms[SBR_N_STAGES]) {
 }
 
 extern "C" int64_t sbr_kernel_launches(const sbr_model* m) { return m ? m->launches : SBR_E_ARG; }
+
+extern "C" int sbr_debug_gemm(sbr_model* m, int engine, int ta, int tb, int M, int N, int K, const float* A, int lda,
+                              const float* B, int ldb, float* C, int ldc, float alpha, float beta, const float* bias,
+                              int reps, float* ms) {
+  CHECK_STICKY(m);
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1 || reps < 1) { sbr_set_error(m, SBR_E_ARG, "debug_gemm: bad arguments"); return SBR_E_ARG; }
+  CU_TRY(m, cudaSetDevice(m->dev));
+  const size_t na = (size_t)(ta ? K : M) * lda, nb = (size_t)(tb ? N : K) * ldb, nc = (size_t)M * ldc;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dbias = nullptr;
+  int rc = 0;
+  if ((rc = dev_alloc(m, &dA, na, false)) || (rc = dev_alloc(m, &dB, nb, false)) || (rc = dev_alloc(m, &dC, nc, false))) return rc;
+  if (bias && (rc = dev_alloc(m, &dbias, (size_t)N, false))) return rc;
+  CU_TRY(m, cudaMemcpyAsync(dA, A, na * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(dB, B, nb * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  if (bias) CU_TRY(m, cudaMemcpyAsync(dbias, bias, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  const bool saved = m->use_tc_gemm;
+  m->use_tc_gemm = engine != 0;
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  CU_TRY(m, cudaEventRecord(m->timer[0], m->stream));
+  for (int r = 0; r < reps && rc == 0; ++r) {
+    if (beta != 0.f || r == 0) CU_TRY(m, cudaMemcpyAsync(dC, C, nc * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    if (bias) {
+      if (engine != 0) { rc = launch_gemm_tc(m, ta != 0, tb != 0, M, N, K, dA, lda, dB, ldb, dC, ldc, alpha, beta, dbias); if (rc == 1) { sbr_set_error(m, SBR_E_ARG, "debug_gemm: tensor-core kernel does not apply"); rc = SBR_E_ARG; } }
+      else rc = launch_gemm_bias(m, tb != 0, M, N, K, dA, lda, dB, ldb, dC, ldc, dbias);
+    } else if (engine != 0) {
+      rc = launch_gemm_tc(m, ta != 0, tb != 0, M, N, K, dA, lda, dB, ldb, dC, ldc, alpha, beta, nullptr);
+      if (rc == 1) { sbr_set_error(m, SBR_E_ARG, "debug_gemm: tensor-core kernel does not apply"); rc = SBR_E_ARG; }
+    } else {
+      rc = launch_gemm(m, ta != 0, tb != 0, M, N, K, dA, lda, dB, ldb, dC, ldc, alpha, beta);
+    }
+  }
+  m->use_tc_gemm = saved;
+  if (rc == 0) {
+    CU_TRY(m, cudaEventRecord(m->timer[1], m->stream));
+    CU_TRY(m, cudaMemcpyAsync(C, dC, nc * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    if (ms) CU_TRY(m, cudaEventElapsedTime(ms, m->timer[0], m->timer[1]));
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); if (dbias) cudaFree(dbias);
+  return rc;
+}
 
 extern "C" int sbr_timer_start(sbr_model* m) {
   CHECK_STICKY(m);

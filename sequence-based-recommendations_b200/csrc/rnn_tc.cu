@@ -1095,6 +1095,7 @@ bool make_map2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols
   }
   if (!fn || !base) return false;
   // the maps only depend on the allocation and the box: encode once (cuTensorMapEncodeTiled costs ~10 us of host time)
+  // (device pointers are unique across the devices of a process under UVA, so the base address identifies the device)
   struct Key { const float* base; uint64_t rows, cols; uint32_t bc, br; CUtensorMap tm; };
   static std::vector<Key> cache;
   for (const Key& k : cache)
@@ -1136,13 +1137,17 @@ int max_active_clusters(Kern kern, const TcPlan& p, size_t smem) {
   return n;
 }
 int resident_clusters(const TcPlan& p) {
-  static int cached_C = -1, cached_n = 0;
-  if (cached_C != p.C) {
-    cached_n = max_active_clusters(rnn_fwd_tc_kernel<4, 8>, p, p.smem);
-    cached_C = p.C;
-    if (getenv("SBR_TC_VERBOSE")) fprintf(stderr, "[tc] clusters of %d CTAs co-resident: %d\n", p.C, cached_n);
-  }
-  return cached_n;
+  // co-resident clusters depend on the device, the cluster size and the shared-memory request: one entry per triple
+  struct Entry { int dev, C; size_t smem; int n; };
+  static std::vector<Entry> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (const Entry& e : cache)
+    if (e.dev == dev && e.C == p.C && e.smem == p.smem) return e.n;
+  const int n = max_active_clusters(rnn_fwd_tc_kernel<4, 8>, p, p.smem);
+  cache.push_back(Entry{dev, p.C, p.smem, n});
+  if (getenv("SBR_TC_VERBOSE")) fprintf(stderr, "[tc] device %d: clusters of %d CTAs co-resident: %d\n", dev, p.C, n);
+  return n;
 }
 // Tile schedule of one scan launch.  The hardware hands clusters to free SM groups in blockIdx order, i.e. list
 // scheduling on `slots` machines (15 eight-CTA clusters fit on a B200: seven GPCs take two, one takes one).  With
@@ -1224,10 +1229,12 @@ int launch_tc(sbr_model* m, Kern kern, const TcPlan& p, int n_tiles, const TcArg
   cudaError_t e = cudaSuccess;
   // raise the opt-in shared-memory limit once per kernel, not on every launch (Kern is the same function-pointer
   // TYPE for every instantiation, so the cache is keyed by the pointer value)
-  static std::vector<std::pair<const void*, size_t>> smem_set;
+  // (the attribute is per device: the cache is keyed by (device, kernel pointer))
+  struct SmemKey { int dev; const void* kern; size_t bytes; };
+  static std::vector<SmemKey> smem_set;
   size_t* have = nullptr;
-  for (auto& kv : smem_set) if (kv.first == (const void*)kern) have = &kv.second;
-  if (!have) { smem_set.push_back({(const void*)kern, 0}); have = &smem_set.back().second; }
+  for (auto& kv : smem_set) if (kv.dev == m->dev && kv.kern == (const void*)kern) have = &kv.bytes;
+  if (!have) { smem_set.push_back(SmemKey{m->dev, (const void*)kern, 0}); have = &smem_set.back().bytes; }
   if (p.smem > *have) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) { sbr_set_error(m, SBR_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SBR_E_CUDA; }

@@ -210,11 +210,11 @@ int launch_wgrad_tc(sbr_model* m, const LayerDesc& L, int rows, float* dW, int l
   splits = cdiv(a.rq_total, per);
   a.rq_per_split = per;
   const size_t smem = (size_t)WG_STAGES * 4 * WG_PART_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::vector<int> attr_devs;      // the opt-in shared-memory limit is a per-device attribute
+  if (std::find(attr_devs.begin(), attr_devs.end(), m->dev) == attr_devs.end()) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { sbr_set_error(m, SBR_E_CUDA, "wgrad_tc attr: %s", cudaGetErrorString(e)); return SBR_E_CUDA; }
-    attr_set = true;
+    attr_devs.push_back(m->dev);
   }
   wgrad_tc_kernel<<<dim3(nts, mts, splits), WG_NT, smem, m->stream>>>(a);
   KERNEL_CHECK(m);
