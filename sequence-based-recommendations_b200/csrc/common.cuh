@@ -160,9 +160,13 @@ struct sbr_model {
   float* step_carry = nullptr;   // [B, maxH]
   float* step_dcs = nullptr;     // [B, maxH]
   float* step_dpe = nullptr;     // [3][B, maxH]
+  unsigned int* scan_sync = nullptr;   // persistent scans (tc_scan.cu): one release/acquire counter per batch tile
+  bool bwd_did_bias = false;     // the last BPTT launcher accumulated the bias gradient itself (else: column sum of dXg)
   // switches read once from the environment at sbr_create (diagnostics / A-B tests)
   bool use_tc_gemm = true;       // SBR_DISABLE_TC_GEMM: FFMA GEMMs everywhere
   bool use_step_scan = true;
+  bool use_persistent_scan = true;   // SBR_DISABLE_PERSISTENT_SCAN: one launch per time step instead of the cooperative scans
+  bool use_tma_gemm = true;      // SBR_DISABLE_TMA_GEMM: cp.async loaders in tc_gemm.cu even where a tensor map is possible
   bool no_side_stream = false, no_early_cost = false, disable_tc = false, disable_tc_bwd = false;   // SBR_NO_SIDE_STREAM, SBR_NO_EARLY_COST, SBR_DISABLE_TC, SBR_DISABLE_TC_BWD     // SBR_DISABLE_STEP_SCAN: FFMA cluster scans for hidden sizes beyond the tcgen05 cluster kernels
 
   // nccl
@@ -214,6 +218,10 @@ int launch_gemm_tc(sbr_model* m, bool ta, bool tb, int M, int N, int K, const fl
 int step_scan_applies(const sbr_model* m, int G, int H);
 int launch_rnn_forward_steps(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last);
 int launch_rnn_backward_steps(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last);
+// tc_scan.cu : the same scans as ONE cooperative launch per layer (return 1 when they do not apply)
+int persistent_scan_applies(const sbr_model* m, int G, int H);
+int launch_rnn_forward_persistent(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last);
+int launch_rnn_backward_persistent(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, const float* dh_last);
 
 // gemm.cu : C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (row-major, beta in {0,1})
 int launch_gemm(sbr_model* m, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,

@@ -220,7 +220,7 @@ extern "C" void sbr_destroy(sbr_model* m) {
   F(m->params); F(m->grads); F(m->opt_a); F(m->opt_b);
   for (LayerDesc& L : m->layers) { F(L.Xg); F(L.act); F(L.hs); F(L.cs); F(L.dXg); F(L.dac); F(L.dhs); F(L.hT); F(L.aT); }
   for (BatchSlot& s : m->slots) { F(s.X); F(s.len); F(s.Y); F(s.pop); }
-  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe);
+  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe); F(m->scan_sync);
   F(m->mY); F(m->mW); F(m->cells); F(m->Wc); F(m->dWc); F(m->bc);
   F(m->tgt_off); F(m->tgt_ids); F(m->w_neg); F(m->def_tgt); F(m->excl_off); F(m->excl_ids); F(m->topk_ids);
   if (m->h_len) cudaFreeHost(m->h_len);
@@ -252,6 +252,8 @@ static int create_impl(sbr_model* m) {
   m->n_sm = prop.multiProcessorCount;
   m->use_tc_gemm = getenv("SBR_DISABLE_TC_GEMM") == nullptr;
   m->use_step_scan = getenv("SBR_DISABLE_STEP_SCAN") == nullptr;
+  m->use_tma_gemm = getenv("SBR_DISABLE_TMA_GEMM") == nullptr;
+  m->use_persistent_scan = getenv("SBR_DISABLE_PERSISTENT_SCAN") == nullptr;
   m->no_side_stream = getenv("SBR_NO_SIDE_STREAM") != nullptr;
   m->no_early_cost = getenv("SBR_NO_EARLY_COST") != nullptr;
   m->disable_tc = getenv("SBR_DISABLE_TC") != nullptr;
@@ -314,6 +316,7 @@ static int create_impl(sbr_model* m) {
       if ((rc = dev_alloc(m, &m->step_carry, B * maxH))) return rc;
       if ((rc = dev_alloc(m, &m->step_dcs, B * maxH))) return rc;
       if ((rc = dev_alloc(m, &m->step_dpe, 3 * B * maxH))) return rc;
+      if ((rc = dev_alloc(m, &m->scan_sync, B / 32 + 8))) return rc;
     }
   }
   if (m->E > 0) {
@@ -661,7 +664,7 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
       if ((rc = launch_gemm(m, true, false, H, GH, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
     }
     // db = sum dXg: the tcgen05 BPTT kernel accumulates it itself; the FFMA fallback needs the column sum
-    if (!(tc_scan_applies(L.G, L.H) && !m->disable_tc && !m->disable_tc_bwd))
+    if (!m->bwd_did_bias)
       if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
     if (li == 0) stage_mark(m, 6);
     if (!gather_layer) {
@@ -1038,10 +1041,11 @@ extern "C" int sbr_debug_gemm(sbr_model* m, int engine, int ta, int tb, int M, i
   if (bias) CU_TRY(m, cudaMemcpyAsync(dbias, bias, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   const bool saved = m->use_tc_gemm;
   m->use_tc_gemm = engine != 0;
+  CU_TRY(m, cudaMemcpyAsync(dC, C, nc * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   CU_TRY(m, cudaEventRecord(m->timer[0], m->stream));
   for (int r = 0; r < reps && rc == 0; ++r) {
-    if (beta != 0.f || r == 0) CU_TRY(m, cudaMemcpyAsync(dC, C, nc * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    if (beta != 0.f && r > 0) CU_TRY(m, cudaMemcpyAsync(dC, C, nc * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     if (bias) {
       if (engine != 0) { rc = launch_gemm_tc(m, ta != 0, tb != 0, M, N, K, dA, lda, dB, ldb, dC, ldc, alpha, beta, dbias); if (rc == 1) { sbr_set_error(m, SBR_E_ARG, "debug_gemm: tensor-core kernel does not apply"); rc = SBR_E_ARG; } }
       else rc = launch_gemm_bias(m, tb != 0, M, N, K, dA, lda, dB, ldb, dC, ldc, dbias);

@@ -618,7 +618,11 @@ int launch_rnn_forward(sbr_model* m, const LayerDesc& L, const int32_t* len, int
     const int rc = launch_rnn_forward_tc(m, L, len, B, t_max, h_last);   // tcgen05 3xTF32 scan when it applies
     if (rc <= 0) return rc;
   }
-  // larger hidden sizes: one tensor-core step kernel per time step (tc_gemm.cu)
+  // larger hidden sizes: the persistent tensor-core scan (tc_scan.cu), else one tensor-core step kernel per time step
+  if (persistent_scan_applies(m, L.G, L.H)) {
+    const int rc = launch_rnn_forward_persistent(m, L, len, B, t_max, h_last);
+    if (rc <= 0) return rc;
+  }
   if (step_scan_applies(m, L.G, L.H)) return launch_rnn_forward_steps(m, L, len, B, t_max, h_last);
   const Plan p = make_plan(m, L.G, L.H, B, false);
   if (p.C == 0) {
@@ -638,11 +642,18 @@ int launch_rnn_forward(sbr_model* m, const LayerDesc& L, const int32_t* len, int
 
 int launch_rnn_backward(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max,
                         const float* dh_last) {
+  m->bwd_did_bias = false;
   if (!m->disable_tc_bwd) {
     const int rc = launch_rnn_backward_tc(m, L, len, B, t_max, dh_last);   // tcgen05 3xTF32 BPTT when it applies
-    if (rc <= 0) return rc;
+    if (rc <= 0) { m->bwd_did_bias = true; return rc; }
   }
-  if (step_scan_applies(m, L.G, L.H) && !tc_scan_applies(L.G, L.H)) return launch_rnn_backward_steps(m, L, len, B, t_max, dh_last);
+  if (!tc_scan_applies(L.G, L.H)) {
+    if (persistent_scan_applies(m, L.G, L.H)) {
+      const int rc = launch_rnn_backward_persistent(m, L, len, B, t_max, dh_last);
+      if (rc <= 0) { m->bwd_did_bias = true; return rc; }
+    }
+    if (step_scan_applies(m, L.G, L.H)) return launch_rnn_backward_steps(m, L, len, B, t_max, dh_last);
+  }
   const Plan p = make_plan(m, L.G, L.H, B, true);
   if (p.C == 0) {
     sbr_set_error(m, SBR_E_ARG, "hidden size %d is not supported by the cluster scan (max 512)", L.H);

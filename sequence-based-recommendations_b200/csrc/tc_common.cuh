@@ -2,8 +2,11 @@
 // allocation / load / store, kind::tf32 MMA in the TS form (A from TMEM, B through a shared-memory descriptor),
 // and the 3xTF32 split.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <vector>
 
 namespace tcx {
 
@@ -71,4 +74,84 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// asynchronous global -> shared copies of 16 / 4 bytes; src_bytes < size zero-fills the rest (0 = pure zero fill)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// the executing thread's prior cp.async copies arrive on the mbarrier when they have landed (counts as one of the
+// barrier's expected arrivals)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one box of a 2-D tiled tensor map -> shared memory; completes (bytes) on the mbarrier
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void split8(const float* v, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float h = tf32_hi(v[i]);
+    hi[i] = __float_as_uint(h);
+    lo[i] = __float_as_uint(v[i] - h);
+  }
+}
+
+// 8 consecutive floats of a row (16-byte aligned): two vector accesses
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 }  // namespace tcx
+
+// ---- tensor maps: 2-D fp32, row pitch ld elements; encoded once per (array, box) and cached
+typedef CUresult (*TcxEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline bool get_tmap(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+              uint32_t box_outer, bool swizzle128) {
+  static TcxEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (TcxEncodeTiledFn)ptr;
+  }
+  if (!fn || !base || (reinterpret_cast<uintptr_t>(base) & 15) || ld % 4 != 0 || inner == 0 || outer == 0 || inner > ld) return false;
+  if (box_inner > 256 || box_outer > 256 || (box_inner * 4) % 16 != 0 || (swizzle128 && box_inner * 4 > 128)) return false;
+  struct Key { const float* base; uint64_t inner, outer, ld; uint32_t bi, bo; bool sw; CUtensorMap tm; };
+  static std::vector<Key> cache;
+  for (const Key& k : cache)
+    if (k.base == base && k.inner == inner && k.outer == outer && k.ld == ld && k.bi == box_inner && k.bo == box_outer && k.sw == swizzle128) {
+      *tm = k.tm;
+      return true;
+    }
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstride[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  if (fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 512) cache.clear();   // arrays of destroyed handles / one-off diagnostics calls
+  cache.push_back(Key{base, inner, outer, ld, box_inner, box_outer, swizzle128, *tm});
+  return true;
+}
+
+

@@ -27,6 +27,8 @@
 //   EPI_*_BWD      one BPTT step: rows = hidden units k, columns = batch rows, D = da_{t+1} W_hid^T; fused gate
 //                  gradients with grad_clip at the reference's sites (sparse_lstm.py:386-388,768-772,789-791).
 //   EPI_INIT_GRAD  the step "t = -1": gradients of the learned initial states and the peepholes.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -36,7 +38,7 @@ namespace {
 
 constexpr int TG_KC = 32;        // k per pipeline stage = 4 MMA k-steps
 constexpr int TG_STAGES = 3;      // converted-operand ring: TMEM slots of A (64 columns each) + shared-memory tiles of B
-constexpr int TG_LOOK = 3;        // chunks each loader thread keeps in flight (thread-private cp.async ring)
+constexpr int TG_LOOK_MAX = 8;    // raw fp32 ring: up to this many 32-wide k chunks in flight (args.look, sized by the shared-memory budget)
 constexpr int TG_NT = 544;       // warps 0-3: A converters + epilogue, 4-7: B converters, 8: MMA issuer, 9-12: A loaders, 13-16: B loaders
 constexpr int TG_A0 = 256;       // first TMEM column of the A ring (D1 | D2 occupy 2*BN <= 256 columns)
 constexpr int STEP_U = 8;        // hidden units per CTA of a forward step (BN = 32 = 4 gates x 8 units)
@@ -67,41 +69,13 @@ struct TgArgs {
   int a_vec, b_vec;
   float* C; long long ldc; float alpha; int accumulate; const float* bias; int c_vec;
   long long* dbg;                                 // optional clock64 timeline of CTA (0,0,0) (SBR_TG_TIMELINE)
+  // raw-ring loaders: TMA tiled loads where the operand allows a tensor map (16-byte aligned base, ld % 4 == 0)
+  CUtensorMap tmA, tmB, tmB2;
+  int tma_a, tma_b;
+  int a_off, b_off, b2_off;                       // row offsets of the tile origin inside the mapped arrays (recurrent steps)
+  int look;                                       // raw ring depth
   StepArgs st;
 };
-
-__device__ __forceinline__ void split8(const float* v, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float h = tf32_hi(v[i]);
-    hi[i] = __float_as_uint(h);
-    lo[i] = __float_as_uint(v[i] - h);
-  }
-}
-
-// asynchronous global -> shared copies of 16 / 4 bytes; src_bytes < size zero-fills the rest (0 = pure zero fill)
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-
-// the executing thread's prior cp.async copies arrive on the mbarrier when they have landed (counts as one of the
-// barrier's expected arrivals)
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-
-// 8 consecutive floats of a row (16-byte aligned): two vector accesses
-__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
 
 template <int EPI>
 __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant__ TgArgs a) {
@@ -109,9 +83,10 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
   __shared__ __align__(8) uint64_t full[TG_STAGES];
   __shared__ __align__(8) uint64_t empty[TG_STAGES];
   __shared__ __align__(8) uint64_t done;
-  __shared__ __align__(8) uint64_t rawA_full[TG_LOOK], rawA_empty[TG_LOOK], rawB_full[TG_LOOK], rawB_empty[TG_LOOK];
+  __shared__ __align__(8) uint64_t rawA_full[TG_LOOK_MAX], rawA_empty[TG_LOOK_MAX], rawB_full[TG_LOOK_MAX], rawB_empty[TG_LOOK_MAX];
   __shared__ uint32_t tmem_base_s;
 
+  uint8_t* const tg_base = tg_smem + ((1024u - (smem_u32(tg_smem) & 1023u)) & 1023u);   // TMA swizzle atoms are 1 KB
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = a.BN;
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
@@ -157,8 +132,9 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
   if (tid == 0) {
     for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
     mbar_init(&done, 1);
-    for (int i = 0; i < TG_LOOK; ++i) {
-      mbar_init(&rawA_full[i], 128); mbar_init(&rawB_full[i], 128);      // one cp.async completion arrive per loader thread
+    for (int i = 0; i < TG_LOOK_MAX; ++i) {
+      // TMA: one arrive.expect_tx by the producer + the bytes; cp.async: one completion arrive per loader thread
+      mbar_init(&rawA_full[i], a.tma_a ? 1 : 128); mbar_init(&rawB_full[i], a.tma_b ? 1 : 128);
       mbar_init(&rawA_empty[i], 4); mbar_init(&rawB_empty[i], 4);        // one arrive per converter warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,12 +153,18 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
 
   // Warp roles.  The threads that wait on global memory (loaders) are NOT the ones that publish operands to the
   // tensor core: fence.proxy.async / tcgen05.wait::st drain the executing thread's outstanding global accesses, so a
-  // thread that both prefetches and publishes pays the full memory latency per stage (measured: 4600 cycles per
-  // 32-wide k chunk).  Loaders only issue cp.async into a raw ring and let the copies arrive on an mbarrier
-  // (cp.async.mbarrier.arrive.noinc); converters only touch shared memory / TMEM.
-  float* rawA = reinterpret_cast<float*>(tg_smem + (size_t)TG_STAGES * stage_bytes);                                  // [TG_LOOK][32][128] floats
-  float4* rawB = reinterpret_cast<float4*>(tg_smem + (size_t)TG_STAGES * stage_bytes + (size_t)TG_LOOK * TG_KC * 128 * 4);   // [TG_LOOK][8][128] float4
-  const bool vecA = a.a_mode == 0 && a.a_vec;
+  // thread that both prefetches and publishes pays the full memory latency per stage.  Loaders fill a raw fp32 ring
+  // (TMA tiled loads issued by one thread when the operand's base / leading dimension allow a tensor map, else
+  // cp.async from 128 threads) and signal an mbarrier; converters only touch shared memory / TMEM.
+  //
+  // Raw tile layouts (the same whichever loader filled them):
+  //   A mode 0  [128 rows][32 k], 128-byte rows with the TMA 128B swizzle: 16-byte chunk q of row r sits at q ^ (r & 7)
+  //   A mode 1  [32 k][128 rows]
+  //   B mode 0  [BN rows][32 k], swizzled like A mode 0;  B mode 1  [32 k][BN];  B mode 2  [gate][32 k][8 units]
+  const int LOOK = a.look;
+  const uint32_t rawA_bytes = 128u * TG_KC * 4u, rawB_bytes = (uint32_t)BN * TG_KC * 4u;
+  uint8_t* rawA0 = tg_base + (size_t)TG_STAGES * stage_bytes;
+  uint8_t* rawB0 = rawA0 + (size_t)LOOK * rawA_bytes;
   auto b_coords = [&](int idx, int& n, int& kq) {
     if (a.b_mode == 0) { n = ((idx >> 6) << 3) + (idx & 7); kq = (idx >> 3) & 7; }
     else { kq = idx / BN; n = idx - kq * BN; }
@@ -194,21 +176,23 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
     long long w_raw = 0, w_empty = 0, w_work = 0;
     TG_T0();
     for (int c = 0; c < n_chunks; ++c) {
-      const int rs = c % TG_LOOK;
-      mbar_wait(&rawA_full[rs], (c / TG_LOOK) & 1);
+      const int rs = c % LOOK;
+      mbar_wait(&rawA_full[rs], (c / LOOK) & 1);
       TG_ACC(w_raw);
       float cur[TG_KC];
-      const float* src = rawA + (size_t)rs * TG_KC * 128;
-      if (vecA) {
+      const float* src = reinterpret_cast<const float*>(rawA0 + (size_t)rs * rawA_bytes);
+      if (a.a_mode == 0) {
 #pragma unroll
         for (int q = 0; q < TG_KC / 4; ++q) {
-          const float4 x = *reinterpret_cast<const float4*>(src + (q * 128 + tid) * 4);
+          const float4 x = *reinterpret_cast<const float4*>(src + tid * 32 + ((q ^ (tid & 7)) << 2));
           cur[4 * q] = x.x; cur[4 * q + 1] = x.y; cur[4 * q + 2] = x.z; cur[4 * q + 3] = x.w;
         }
       } else {
 #pragma unroll
         for (int i = 0; i < TG_KC; ++i) cur[i] = src[i * 128 + tid];
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rawA_empty[rs]);       // the raw cells are in registers
       const int s = c % TG_STAGES;
       if (c >= TG_STAGES) {
         mbar_wait(&empty[s], ((c / TG_STAGES) - 1) & 1);
@@ -226,7 +210,7 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&full[s]); mbar_arrive(&rawA_empty[rs]); }   // the raw cells are in registers / TMEM
+      if (lane == 0) mbar_arrive(&full[s]);
       TG_ACC(w_work);
     }
     if (tl && tid == 0) { a.dbg[0] = w_raw; a.dbg[1] = w_empty; a.dbg[2] = w_work; a.dbg[3] = clock64() - t_start; }
@@ -237,20 +221,33 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
     long long w_raw = 0, w_empty = 0, w_work = 0;
     TG_T0();
     for (int c = 0; c < n_chunks; ++c) {
-      const int rs = c % TG_LOOK;
-      mbar_wait(&rawB_full[rs], (c / TG_LOOK) & 1);
+      const int rs = c % LOOK;
+      mbar_wait(&rawB_full[rs], (c / LOOK) & 1);
       TG_ACC(w_raw);
-      const float4* src = rawB + (size_t)rs * 8 * 128;
+      const float* src = reinterpret_cast<const float*>(rawB0 + (size_t)rs * rawB_bytes);
       float4 cur[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         if (it >= per) break;
-        cur[it] = src[it * 128 + bt];
+        int n, kq;
+        b_coords(it * 128 + bt, n, kq);
+        if (a.b_mode == 0) {
+          cur[it] = *reinterpret_cast<const float4*>(src + n * 32 + ((kq ^ (n & 7)) << 2));
+        } else if (a.b_mode == 1) {
+          const float* q = src + (4 * kq) * BN + n;
+          cur[it] = make_float4(q[0], q[BN], q[2 * BN], q[3 * BN]);
+        } else {
+          const int g = n / STEP_U, j = n - g * STEP_U;
+          const float* q = src + g * (TG_KC * STEP_U) + (4 * kq) * STEP_U + j;
+          cur[it] = g < a.st.G ? make_float4(q[0], q[STEP_U], q[2 * STEP_U], q[3 * STEP_U]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rawB_empty[rs]);
       const int s = c % TG_STAGES;
       if (c >= TG_STAGES) mbar_wait(&empty[s], ((c / TG_STAGES) - 1) & 1);
       TG_ACC(w_empty);
-      uint8_t* st = tg_smem + (size_t)s * stage_bytes;
+      uint8_t* st = tg_base + (size_t)s * stage_bytes;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         if (it >= per) break;
@@ -266,7 +263,7 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
       }
       proxy_fence_smem();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&full[s]); mbar_arrive(&rawB_empty[rs]); }
+      if (lane == 0) mbar_arrive(&full[s]);
       TG_ACC(w_work);
     }
     if (tl && tid == 128) { a.dbg[8] = w_raw; a.dbg[9] = w_empty; a.dbg[10] = w_work; a.dbg[11] = clock64() - t_start; }
@@ -283,7 +280,7 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
         mbar_wait(&full[s], (c / TG_STAGES) & 1);
         tc_fence_after();
         TG_ACC(w_full);
-        const uint32_t sb = smem_u32(tg_smem + (size_t)s * stage_bytes);
+        const uint32_t sb = smem_u32(tg_base + (size_t)s * stage_bytes);
         const uint32_t ta = tA + (uint32_t)s * 64u;
 #pragma unroll
         for (int ks = 0; ks < TG_KC / 8; ++ks) {
@@ -302,69 +299,117 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
     }
     __syncwarp();
     } else if (warp < 13) {
-    // =================================================================================== A loader (thread <-> row)
+    // =================================================================================== A loader
     const int r = tid - 9 * 32;
-    const int row = m0 + r;
-    const bool row_ok = row < a.M;
     long long w_wait = 0, w_work = 0;
     TG_T0();
-    for (int c = 0; c < n_chunks; ++c) {
-      const int rs = c % TG_LOOK;
-      if (c >= TG_LOOK) mbar_wait(&rawA_empty[rs], ((c / TG_LOOK) - 1) & 1);
-      TG_ACC(w_wait);
-      const int k0 = k_begin + c * TG_KC;
-      float* dst = rawA + (size_t)rs * TG_KC * 128;
-      if (vecA) {
-        const float* src = a.A + (long long)row * a.lda + k0;
-#pragma unroll
-        for (int q = 0; q < TG_KC / 4; ++q) {
-          const int left = row_ok ? (k_end - (k0 + 4 * q)) * 4 : 0;
-          const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
-          cp_async16(dst + (q * 128 + r) * 4, nb > 0 ? src + 4 * q : a.A, nb);
-        }
-      } else if (a.a_mode == 0) {
-        const float* src = a.A + (long long)row * a.lda + k0;
-#pragma unroll
-        for (int i = 0; i < TG_KC; ++i) {
-          const bool ok = row_ok && k0 + i < k_end;
-          cp_async4(dst + i * 128 + r, ok ? src + i : a.A, ok ? 4 : 0);
-        }
-      } else {
-        const float* src = a.A + (long long)k0 * a.lda + row;
-#pragma unroll
-        for (int i = 0; i < TG_KC; ++i) {
-          const bool ok = row_ok && k0 + i < k_end;
-          cp_async4(dst + i * 128 + r, ok ? src + (long long)i * a.lda : a.A, ok ? 4 : 0);
+    if (a.tma_a) {
+      // ---- TMA producer: ONE thread issues the tiled loads of the A operand
+      if (r == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&a.tmA) : "memory");
+        for (int c = 0; c < n_chunks; ++c) {
+          const int rs = c % LOOK;
+          if (c >= LOOK) mbar_wait(&rawA_empty[rs], ((c / LOOK) - 1) & 1);
+          TG_ACC(w_wait);
+          const int k0 = k_begin + c * TG_KC;
+          mbar_arrive_expect_tx(&rawA_full[rs], rawA_bytes);
+          if (a.a_mode == 0) tma_load_2d(rawA0 + (size_t)rs * rawA_bytes, &a.tmA, k0, a.a_off + m0, &rawA_full[rs]);
+          else tma_load_2d(rawA0 + (size_t)rs * rawA_bytes, &a.tmA, a.a_off + m0, k0, &rawA_full[rs]);
+          TG_ACC(w_work);
         }
       }
-      cp_async_arrive(&rawA_full[rs]);
-      TG_ACC(w_work);
+    }
+    if (!a.tma_a) {
+      // ---- cp.async fallback (unaligned base / leading dimension): thread r copies row r's cells
+      const int row = m0 + r;
+      const bool row_ok = row < a.M;
+      const bool vec = a.a_mode == 0 && a.a_vec;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int rs = c % LOOK;
+        if (c >= LOOK) mbar_wait(&rawA_empty[rs], ((c / LOOK) - 1) & 1);
+        TG_ACC(w_wait);
+        const int k0 = k_begin + c * TG_KC;
+        float* dst = reinterpret_cast<float*>(rawA0 + (size_t)rs * rawA_bytes);
+        if (vec) {
+          const float* src = a.A + (long long)(a.a_off + row) * a.lda + k0;
+#pragma unroll
+          for (int q = 0; q < TG_KC / 4; ++q) {
+            const int left = row_ok ? (k_end - (k0 + 4 * q)) * 4 : 0;
+            const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+            cp_async16(dst + r * 32 + ((q ^ (r & 7)) << 2), nb > 0 ? src + 4 * q : a.A, nb);
+          }
+        } else if (a.a_mode == 0) {
+          const float* src = a.A + (long long)(a.a_off + row) * a.lda + k0;
+#pragma unroll
+          for (int i = 0; i < TG_KC; ++i) {
+            const bool ok = row_ok && k0 + i < k_end;
+            cp_async4(dst + r * 32 + (((i >> 2) ^ (r & 7)) << 2) + (i & 3), ok ? src + i : a.A, ok ? 4 : 0);
+          }
+        } else {
+          const float* src = a.A + (long long)k0 * a.lda + a.a_off + row;
+#pragma unroll
+          for (int i = 0; i < TG_KC; ++i) {
+            const bool ok = row_ok && k0 + i < k_end;
+            cp_async4(dst + i * 128 + r, ok ? src + (long long)i * a.lda : a.A, ok ? 4 : 0);
+          }
+        }
+        cp_async_arrive(&rawA_full[rs]);
+        TG_ACC(w_work);
+      }
     }
     if (tl && r == 0) { a.dbg[24] = w_wait; a.dbg[25] = w_work; a.dbg[26] = clock64() - t_start; }
+  } else if (a.tma_b) {
+    // =================================================================================== B loader: TMA producer (one thread)
+    if (tid == 13 * 32) {
+      long long w_wait = 0, w_work = 0;
+      TG_T0();
+      asm volatile("prefetch.tensormap [%0];" :: "l"(&a.tmB) : "memory");
+      for (int c = 0; c < n_chunks; ++c) {
+        const int rs = c % LOOK;
+        if (c >= LOOK) mbar_wait(&rawB_empty[rs], ((c / LOOK) - 1) & 1);
+        TG_ACC(w_wait);
+        const int k0 = k_begin + c * TG_KC;
+        uint8_t* dst = rawB0 + (size_t)rs * rawB_bytes;
+        if (a.b_mode == 0) {
+          mbar_arrive_expect_tx(&rawB_full[rs], rawB_bytes);
+          if (a.B2 && k0 >= a.b_split) tma_load_2d(dst, &a.tmB2, k0 - a.b_split, a.b2_off + n0, &rawB_full[rs]);
+          else tma_load_2d(dst, &a.tmB, k0, a.b_off + n0, &rawB_full[rs]);
+        } else if (a.b_mode == 1) {
+          mbar_arrive_expect_tx(&rawB_full[rs], rawB_bytes);
+          tma_load_2d(dst, &a.tmB, a.b_off + n0, k0, &rawB_full[rs]);
+        } else {
+          mbar_arrive_expect_tx(&rawB_full[rs], (uint32_t)a.st.G * TG_KC * STEP_U * 4u);
+          for (int g = 0; g < a.st.G; ++g)
+            tma_load_2d(dst + g * (TG_KC * STEP_U * 4), &a.tmB, g * a.st.H + (int)blockIdx.x * STEP_U, k0, &rawB_full[rs]);
+        }
+        TG_ACC(w_work);
+      }
+      if (tl) { a.dbg[32] = w_wait; a.dbg[33] = w_work; a.dbg[34] = clock64() - t_start; }
+    }
   } else {
-    // =================================================================================== B loader
+    // =================================================================================== B loader (cp.async fallback)
     const int bt = tid - 13 * 32;
     const int per = BN / 16;
     long long w_wait = 0, w_work = 0;
     TG_T0();
     for (int c = 0; c < n_chunks; ++c) {
-      const int rs = c % TG_LOOK;
-      if (c >= TG_LOOK) mbar_wait(&rawB_empty[rs], ((c / TG_LOOK) - 1) & 1);
+      const int rs = c % LOOK;
+      if (c >= LOOK) mbar_wait(&rawB_empty[rs], ((c / LOOK) - 1) & 1);
       TG_ACC(w_wait);
       const int k0 = k_begin + c * TG_KC;
-      float4* dst = rawB + (size_t)rs * 8 * 128;
+      float* dst = reinterpret_cast<float*>(rawB0 + (size_t)rs * rawB_bytes);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         if (it >= per) break;
         int n, kq;
         b_coords(it * 128 + bt, n, kq);
         const int k = k0 + 4 * kq;
-        float* cell = reinterpret_cast<float*>(dst + it * 128 + bt);
         if (a.b_mode == 0) {
+          float* cell = dst + n * 32 + ((kq ^ (n & 7)) << 2);
           const bool ok = n0 + n < a.N && k < k_end;
           const float* src = a.B;
-          if (ok) src = (a.B2 && k >= a.b_split) ? a.B2 + (long long)(n0 + n) * a.ldb2 + (k - a.b_split)
-                                                 : a.B + (long long)(n0 + n) * a.ldb + k;
+          if (ok) src = (a.B2 && k >= a.b_split) ? a.B2 + (long long)(a.b2_off + n0 + n) * a.ldb2 + (k - a.b_split)
+                                                 : a.B + (long long)(a.b_off + n0 + n) * a.ldb + k;
           if (a.b_vec) {
             const int left = ok ? (k_end - k) * 4 : 0;
             cp_async16(cell, src, left >= 16 ? 16 : (left > 0 ? left : 0));
@@ -374,14 +419,27 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
           }
         } else {
           long long col = -1;
-          if (a.b_mode == 1) { if (n0 + n < a.N) col = n0 + n; }
-          else {
+          float* cell;
+          if (a.b_mode == 1) {
+            if (n0 + n < a.N) col = a.b_off + n0 + n;
+            cell = dst + (4 * kq) * BN + n;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool oe = col >= 0 && k + e < k_end;
+              cp_async4(cell + e * BN, oe ? a.B + (long long)(k + e) * a.ldb + col : a.B, oe ? 4 : 0);
+            }
+          } else {
             const int g = n / STEP_U, j = n - g * STEP_U, u = blockIdx.x * STEP_U + j;
             if (g < a.st.G && u < a.st.H) col = (long long)g * a.st.H + u;
-          }
-          const float* src = a.B + (long long)k * a.ldb + (col >= 0 ? col : 0);
+            cell = dst + g * (TG_KC * STEP_U) + (4 * kq) * STEP_U + j;
+            if (g < 4) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { const bool oe = col >= 0 && k + e < k_end; cp_async4(cell + e, oe ? src + (long long)e * a.ldb : a.B, oe ? 4 : 0); }
+              for (int e = 0; e < 4; ++e) {
+                const bool oe = col >= 0 && k + e < k_end;
+                cp_async4(cell + e * STEP_U, oe ? a.B + (long long)(k + e) * a.ldb + col : a.B, oe ? 4 : 0);
+              }
+            }
+          }
         }
       }
       cp_async_arrive(&rawB_full[rs]);
@@ -621,15 +679,23 @@ __global__ void zero2d_kernel(float* C, int M, int N, long long ldc) {
   C[(i / N) * ldc + (i % N)] = 0.f;
 }
 
+constexpr size_t TG_SMEM_MAX = 232448 - 1024;      // 227 KB opt-in limit minus the static barriers
+
+size_t tg_conv_bytes(int BN) { return (size_t)TG_STAGES * BN * TG_KC * 8; }
+size_t tg_raw_stage_bytes(int BN) { return (size_t)128 * TG_KC * 4 + (size_t)BN * TG_KC * 4; }
+int tg_look(int BN) {
+  const size_t left = TG_SMEM_MAX - 1024 - tg_conv_bytes(BN);
+  return (int)std::max<size_t>(2, std::min<size_t>(TG_LOOK_MAX, left / tg_raw_stage_bytes(BN)));
+}
+
 template <int EPI>
 int launch_tg(sbr_model* m, const TgArgs& a, dim3 grid) {
-  // converted B ring + thread-private raw rings of the A loaders ([LOOK][32][128] floats) and B loaders ([LOOK][8][128] float4)
-  const size_t smem = (size_t)TG_STAGES * a.BN * TG_KC * 8 + (size_t)TG_LOOK * TG_KC * 128 * 4 + (size_t)TG_LOOK * 8 * 128 * 16;
+  // converted B ring + raw fp32 ring (A tile 16 KB + B tile BN*128 B per stage) + 1 KB alignment slack
+  const size_t smem = tg_conv_bytes(a.BN) + (size_t)a.look * tg_raw_stage_bytes(a.BN) + 1024;
   // opt-in shared-memory limit: per (kernel instantiation, device) -- the attribute is per device
   static std::vector<int> done_dev;
   if (std::find(done_dev.begin(), done_dev.end(), m->dev) == done_dev.end()) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TG_STAGES * 128 * TG_KC * 8 + TG_LOOK * TG_KC * 128 * 4 + TG_LOOK * 8 * 128 * 16);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
     if (e != cudaSuccess) { sbr_set_error(m, SBR_E_CUDA, "tc_gemm attr: %s", cudaGetErrorString(e)); return SBR_E_CUDA; }
     done_dev.push_back(m->dev);
   }
@@ -658,6 +724,11 @@ int launch_gemm_tc(sbr_model* m, bool ta, bool tb, int M, int N, int K, const fl
   a.b_vec = (tb && ldb % 4 == 0 && aligned16(B)) ? 1 : 0;
   a.C = C; a.ldc = ldc; a.alpha = alpha; a.accumulate = beta == 1.f ? 1 : 0; a.bias = bias;
   a.c_vec = (ldc % 4 == 0 && aligned16(C)) ? 1 : 0;
+  a.look = tg_look(a.BN);
+  if (m->use_tma_gemm) {
+    a.tma_a = ta ? get_tmap(&a.tmA, A, M, K, lda, 128, TG_KC, false) : get_tmap(&a.tmA, A, K, M, lda, TG_KC, 128, true);
+    a.tma_b = tb ? get_tmap(&a.tmB, B, K, N, ldb, TG_KC, a.BN, true) : get_tmap(&a.tmB, B, N, K, ldb, a.BN, TG_KC, false);
+  }
   const int tiles = cdiv(M, 128) * cdiv(N, a.BN);
   int splits = 1;
   if (tiles < m->n_sm) splits = std::max(1, std::min(m->n_sm / tiles, K / 256));   // tall-K, small output: fill the SMs
@@ -694,7 +765,8 @@ int launch_gemm_tc(sbr_model* m, bool ta, bool tb, int M, int N, int K, const fl
 // 1 when the per-step tensor-core scan handles this layer (hidden sizes beyond the cluster-resident kernels)
 int step_scan_applies(const sbr_model* m, int G, int H) {
   (void)G;
-  return (m->use_tc_gemm && m->use_step_scan && H % 8 == 0 && H >= 32) ? 1 : 0;
+  // H % 16: the GRU backward switches its B source (dXg | dac) at k = 2H, which must be a 32-wide chunk boundary
+  return (m->use_tc_gemm && m->use_step_scan && H % 16 == 0 && H >= 32) ? 1 : 0;
 }
 
 int launch_rnn_forward_steps(sbr_model* m, const LayerDesc& L, const int32_t* len, int B, int t_max, float* h_last) {
@@ -710,10 +782,16 @@ int launch_rnn_forward_steps(sbr_model* m, const LayerDesc& L, const int32_t* le
   a.lda = H; a.a_mode = 0; a.a_vec = 1;
   a.B = m->params + L.W_hid; a.ldb = GH; a.b_mode = 2;
   a.M = B; a.N = STEP_BN; a.K = H; a.BN = STEP_BN; a.k_per_split = (int)round_up(H, TG_KC);
+  a.look = tg_look(a.BN);
+  a.A = L.hs;
+  if (m->use_tma_gemm) {
+    a.tma_a = get_tmap(&a.tmA, L.hs, H, (uint64_t)(m->T + 1) * m->B, H, TG_KC, 128, true);
+    a.tma_b = get_tmap(&a.tmB, m->params + L.W_hid, GH, H, GH, STEP_U, TG_KC, false);
+  }
   a.st.B = B; a.st.H = H; a.st.G = G; a.st.len = len; a.st.peep = m->params + L.peep;
   const dim3 grid(cdiv(H, STEP_U), cdiv(B, 128), 1);
   for (int t = 0; t < t_max; ++t) {
-    a.A = L.hs + (int64_t)t * B * H;
+    a.a_off = t * B;       // rows t*B .. of the state trajectory
     a.st.t = t;
     a.st.Xg_t = L.Xg + (int64_t)t * B * GH;
     a.st.hs_t = L.hs + (int64_t)t * B * H;
@@ -748,6 +826,14 @@ int launch_rnn_backward_steps(sbr_model* m, const LayerDesc& L, const int32_t* l
   a.A = m->params + L.W_hid; a.lda = GH; a.a_mode = 0; a.a_vec = 1;
   a.b_mode = 0; a.b_vec = 1;
   a.M = H; a.N = B; a.K = GH; a.BN = STEP_BN; a.k_per_split = (int)round_up(GH, TG_KC);
+  a.look = tg_look(a.BN);
+  a.B = L.dXg; a.ldb = GH;
+  if (G == 3) { a.B2 = L.dac; a.ldb2 = H; a.b_split = 2 * H; }
+  if (m->use_tma_gemm) {
+    a.tma_a = get_tmap(&a.tmA, m->params + L.W_hid, GH, H, GH, TG_KC, 128, true);
+    a.tma_b = get_tmap(&a.tmB, L.dXg, GH, (uint64_t)m->T * m->B, GH, TG_KC, STEP_BN, true);
+    if (G == 3) a.tma_b = a.tma_b && get_tmap(&a.tmB2, L.dac, H, (uint64_t)m->T * m->B, H, TG_KC, STEP_BN, true);
+  }
   StepArgs& s = a.st;
   s.B = B; s.H = H; s.G = G; s.len = len; s.peep = m->params + L.peep; s.clip = m->cfg.grad_clip;
   s.carry = m->step_carry; s.dcs = m->step_dcs; s.dpe = m->step_dpe;
@@ -756,11 +842,10 @@ int launch_rnn_backward_steps(sbr_model* m, const LayerDesc& L, const int32_t* l
   for (int t = t_max - 1; t >= -1; --t) {
     // B operand = da_{t+1}: dXg rows of step t+1 (GRU: the candidate's hidden pre-activation gradient comes from dac)
     if (t + 1 < t_max) {
-      a.B = L.dXg + (int64_t)(t + 1) * B * GH; a.ldb = GH;
-      if (G == 3) { a.B2 = L.dac + (int64_t)(t + 1) * B * H; a.ldb2 = H; a.b_split = 2 * H; }
+      a.b_off = a.b2_off = (t + 1) * B;
       a.K = GH;
     } else {
-      a.B = L.dXg; a.ldb = GH; a.B2 = nullptr; a.K = 0;        // first step: nothing flows in from t+1
+      a.b_off = a.b2_off = 0; a.K = 0;        // first step: nothing flows in from t+1
     }
     s.t = t;
     int rc;

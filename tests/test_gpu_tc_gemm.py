@@ -71,6 +71,31 @@ def test_gemm_small_magnitudes_keep_relative_accuracy(eng):
     assert np.abs(C - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+def test_cp_async_loaders_match_the_tma_loaders(monkeypatch):
+    """SBR_DISABLE_TMA_GEMM: the raw ring is filled by cp.async from 128 threads per operand instead of TMA tiled loads
+    (the path unaligned operands take); same raw layouts, same results."""
+    from sbr_b200 import _capi
+    rng = np.random.RandomState(11)
+    cases = []
+    for ta, tb, M, N, K in [(False, True, 300, 260, 512), (True, False, 256, 96, 1000), (False, False, 200, 1024, 256), (True, True, 64, 48, 96)]:
+        A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+        B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+        cases.append((ta, tb, A, B))
+    outs = []
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("SBR_DISABLE_TMA_GEMM", env)
+        e = _capi.Engine(n_items=16, cell="GRU", layers=(8,), max_length=4, batch_size=2)
+        try:
+            outs.append([e.debug_gemm(A, B, ta=ta, tb=tb, engine=1)[0] for ta, tb, A, B in cases])
+        finally:
+            e.close()
+    for (ta, tb, A, B), c_tma, c_cp in zip(cases, *outs):
+        ref = _ref(A, B, ta, tb)
+        assert np.abs(c_tma - ref).max() <= 1e-5 * np.sqrt(A.shape[0] if ta else A.shape[1]) + 1e-6
+        np.testing.assert_array_equal(c_tma, c_cp)       # same arithmetic, different loaders
+
+
 def test_ffma_and_tensor_core_engines_agree(eng):
     rng = np.random.RandomState(9)
     A = rng.standard_normal((500, 300)).astype(np.float32)
@@ -83,10 +108,14 @@ def test_ffma_and_tensor_core_engines_agree(eng):
 # ---------------------------------------------------------------------------------------- per-step tensor-core scans
 @pytest.mark.parametrize("cell,layers,B,T", [("LSTM", (256,), 160, 7), ("GRU", (512,), 130, 6), ("LSTM", (256, 256), 140, 6),
                                              ("GRU", (512, 512), 256, 5), ("Vanilla", (320,), 40, 6), ("LSTM", (512,), 33, 5),
-                                             ("GRU", (232,), 64, 6)])
-def test_step_scans_match_oracle(cell, layers, B, T):
-    """H > 224 (and any H % 8 == 0 the cluster kernels do not take): one tcgen05 step kernel per time step, forward
-    and BPTT; batch sizes that are not multiples of the 128-row / 32-column tiles."""
+                                             ("GRU", (240,), 64, 6)])
+@pytest.mark.parametrize("persistent", [True, False])
+def test_step_scans_match_oracle(cell, layers, B, T, persistent, monkeypatch):
+    """H > 224 (H % 16 == 0): the persistent cooperative tensor-core scans (tc_scan.cu, one launch per layer), or with
+    SBR_DISABLE_PERSISTENT_SCAN one tcgen05 step kernel per time step (tc_gemm.cu); forward and BPTT; batch sizes that
+    are not multiples of the 128-row / 32-column tiles."""
+    if not persistent:
+        monkeypatch.setenv("SBR_DISABLE_PERSISTENT_SCAN", "1")
     spec = O.Spec(n_items=173, cell=cell, layers=layers, loss="CCE")
     check_grads(spec, B=B, T=T, seed=len(layers) + B)
 
@@ -111,6 +140,7 @@ def test_step_scans_really_run_and_agree_with_the_ffma_fallback(monkeypatch):
         finally:
             e.close()
 
+    monkeypatch.setenv("SBR_DISABLE_PERSISTENT_SCAN", "1")
     c1, g1, n1 = run()
     monkeypatch.setenv("SBR_DISABLE_STEP_SCAN", "1")
     c0, g0, n0 = run()
