@@ -134,6 +134,15 @@ SBR_API int sbr_train_step_margin(sbr_model* m, const int32_t* X, const float* m
                           const float* w_neg /* [B] */, const float* default_target /* [n_items] or NULL */,
                           int exclude_seen, int B, float* cost);
 
+/* Device-side batch assembly (replaces the per-item python loop of rnn_one_hot.py:90-101 /
+ * rnn_base.py:396-415): upload the training sequences ONCE as a CSR of ids ([total, ids_per_step] int32, offsets
+ * [n_seqs+1]); a mini-batch is then B (sequence, start, length) triples -- row b reads
+ * ids[offsets[seq_b] + start_b : + len_b] -- and the padded X / lengths are built on the device.  Same arithmetic and
+ * same results as sbr_train_step_cce on the equivalent X / mask. */
+SBR_API int sbr_dataset_upload(sbr_model* m, int n_seqs, const int32_t* offsets, const int32_t* ids);
+SBR_API int sbr_train_step_cce_rows(sbr_model* m, const int32_t* seq, const int32_t* start, const int32_t* len,
+                                    const int32_t* Y, const float* pop, int B, float* cost);
+
 /* Device-resident batches (bench `value`, prefetch): stage a batch into slot s once, then step on
  * it any number of times with no host->device traffic.  cost may be NULL (no sync, no D2H). */
 SBR_API int sbr_stage_cce(sbr_model* m, int slot, const int32_t* X, const float* mask, const int32_t* Y,

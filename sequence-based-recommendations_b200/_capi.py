@@ -71,6 +71,8 @@ SIGNATURES = {
     "sbr_train_step_sampled": (C.c_int, [_P, _i32p, _f32p, _i32p, C.c_int, C.c_int, _i32p, C.c_int, _f32p, C.c_int, _f32p]),
     "sbr_train_step_margin_dense": (C.c_int, [_P, _i32p, _f32p, _f32p, _f32p, C.c_int, _f32p]),
     "sbr_train_step_margin": (C.c_int, [_P, _i32p, _f32p, _i32p, _i32p, _f32p, _f32p, C.c_int, C.c_int, _f32p]),
+    "sbr_dataset_upload": (C.c_int, [_P, C.c_int, _i32p, _i32p]),
+    "sbr_train_step_cce_rows": (C.c_int, [_P, _i32p, _i32p, _i32p, _i32p, _f32p, C.c_int, _f32p]),
     "sbr_stage_cce": (C.c_int, [_P, C.c_int, _i32p, _f32p, _i32p, _f32p, C.c_int]),
     "sbr_train_step_staged": (C.c_int, [_P, C.c_int, _f32p]),
     "sbr_synchronize": (C.c_int, [_P, _f32p]),
@@ -290,6 +292,24 @@ class Engine(object):
                                                    _ptr(ids, _i32p), _ptr(w, _f32p),
                                                    None if dt is None else _ptr(dt, _f32p),
                                                    int(bool(exclude_seen)), B, C.byref(cost)))
+        return np.float32(cost.value)
+
+    # -- device-side batch assembly ---------------------------------------------------------------
+    def dataset_upload(self, offsets, ids):
+        """The training sequences as a CSR of ids: offsets [n+1], ids [total, ids_per_step]."""
+        off = _i32(offsets)
+        ids = _i32(ids).reshape(-1, self.ids_per_step)
+        if ids.shape[0] != off[-1]:
+            raise ValueError("ids has %d rows, offsets end at %d" % (ids.shape[0], off[-1]))
+        if ids.size == 0:
+            ids = np.zeros((1, self.ids_per_step), dtype=np.int32)
+        self._check(self.lib.sbr_dataset_upload(self._h, len(off) - 1, _ptr(off, _i32p), _ptr(np.ascontiguousarray(ids), _i32p)))
+
+    def train_step_cce_rows(self, seq, start, length, Y, pop):
+        seq, start, length, Y, pop = _i32(seq), _i32(start), _i32(length), _i32(Y), _f32(pop)
+        cost = C.c_float(0)
+        self._check(self.lib.sbr_train_step_cce_rows(self._h, _ptr(seq, _i32p), _ptr(start, _i32p), _ptr(length, _i32p),
+                                                     _ptr(Y, _i32p), _ptr(pop, _f32p), len(seq), C.byref(cost)))
         return np.float32(cost.value)
 
     # -- device-resident batches ----------------------------------------------------------------

@@ -149,6 +149,12 @@ struct sbr_model {
   int32_t* excl_ids = nullptr;
   int excl_cap = 0;
   int32_t* topk_ids = nullptr;
+  // device-side batch assembly: the training sequences as a CSR of ids
+  int32_t* ds_off = nullptr;          // [ds_n + 1]
+  int32_t* ds_ids = nullptr;          // [total, K]
+  int32_t* ds_rows = nullptr;         // [3, B] (sequence, start, length) triples of the current batch
+  int ds_n = 0;
+  std::vector<int32_t> ds_hoff;       // host copy of the offsets (argument validation)
   // host staging (pinned)
   int32_t* h_len = nullptr;
   const int32_t* cur_hlen = nullptr;  // host lengths of the batch being processed (BatchSlot::hlen), may be null
@@ -166,11 +172,15 @@ struct sbr_model {
   bool use_tc_gemm = true;       // SBR_DISABLE_TC_GEMM: FFMA GEMMs everywhere
   bool use_step_scan = true;
   bool use_persistent_scan = true;   // SBR_DISABLE_PERSISTENT_SCAN: one launch per time step instead of the cooperative scans
+  bool use_splitk_scan = true;   // SBR_DISABLE_SPLITK_SCAN: one CTA per BPTT tile instead of a split-K cluster of 4
+  int scan_fence_mode = 3;       // SBR_SCAN_FENCE: how the persistent scans publish a step (tc_scan.cu::publish_step)
   bool use_tma_gemm = true;      // SBR_DISABLE_TMA_GEMM: cp.async loaders in tc_gemm.cu even where a tensor map is possible
   bool no_side_stream = false, no_early_cost = false, disable_tc = false, disable_tc_bwd = false;   // SBR_NO_SIDE_STREAM, SBR_NO_EARLY_COST, SBR_DISABLE_TC, SBR_DISABLE_TC_BWD     // SBR_DISABLE_STEP_SCAN: FFMA cluster scans for hidden sizes beyond the tcgen05 cluster kernels
 
   // nccl
   void* nccl_comm = nullptr;
+  bool grads_from_nccl = false;       // gradient arena allocated by ncclMemAlloc and registered with the communicator
+  void* nccl_reg_handle = nullptr;
 
   // profiling
   bool profiling = false;
@@ -240,6 +250,10 @@ int launch_sampling_loss(sbr_model* m, int loss, bool tanh_out, float* A, int ld
                          float* row_loss);
 int launch_margin_loss(sbr_model* m, int loss, float* pred, int ld, const float* bias, const float* Y,
                        const float* W, int B, int N, float inv_global_batch, float* row_loss);
+int launch_margin_loss_ragged(sbr_model* m, int loss, float* pred, int ld, const float* bias, const int32_t* toff,
+                              const int32_t* tids, const int32_t* X, const int32_t* len, const float* w_neg,
+                              const float* def_tgt, int exclude_seen, int B, int T, int K, int N, int max_special,
+                              float inv_gb, float* row_loss);
 int launch_margin_fill(sbr_model* m, float* Y, float* W, const int32_t* X, const int32_t* len, const int32_t* toff,
                        const int32_t* tids, const float* w_neg, const float* def_tgt, int exclude_seen, int B,
                        int T, int K, int N);

@@ -223,6 +223,74 @@ __global__ void __launch_bounds__(LT) margin_loss_kernel(int loss, float* __rest
   if (threadIdx.x == 0) row_loss[b] = l * inv_gb;
 }
 
+// one element of a margin loss (rnn_margin.py:61-68): contribution to the row loss and d loss / d pred
+__device__ __forceinline__ void margin_elem(int loss, float p, float yt, float wt, float& l, float& d) {
+  if (loss == SBR_LOSS_HINGE) {
+    const float z = (p - yt) * wt;
+    l = fmaxf(z, 0.f);
+    d = (z > 0.f ? 1.f : (z == 0.f ? 0.5f : 0.f)) * wt;   // theano relu = 0.5 (x + |x|)
+  } else if (loss == SBR_LOSS_LOGIT) {
+    const float sg = sigm(p - yt);
+    l = sg * wt;
+    d = sg * (1.f - sg) * wt;
+  } else {
+    const float z = (yt - p) * wt;
+    l = softplus(-z);            // -log sigmoid(z)
+    d = (1.f - sigm(z)) * wt;
+  }
+}
+
+// The same loss straight from the ragged description of a row (rnn_margin.py:121-149 builds dense [B, n_items] target
+// and weight matrices on the host; they are never materialised here): weight = w_neg[b], target = default everywhere,
+// except the row's targets (target 1, weight -1) and -- after them, so they win -- the items of its input window
+// (target 0, weight 0).  The S = n_targets + len special entries keep their original prediction in shared memory
+// while the dense pass overwrites the row with the default gradient; then every DISTINCT special id is corrected once
+// by its last entry in the list (targets first, seen items second: the reference's override order).
+__global__ void __launch_bounds__(LT) margin_loss_ragged_kernel(int loss, float* __restrict__ pred, int ld, const float* __restrict__ bias,
+                                                                 const int32_t* __restrict__ toff, const int32_t* __restrict__ tids,
+                                                                 const int32_t* __restrict__ X, const int32_t* __restrict__ len,
+                                                                 const float* __restrict__ w_neg, const float* __restrict__ def_tgt,
+                                                                 int exclude_seen, int T, int K, int N, float inv_gb,
+                                                                 float* __restrict__ row_loss) {
+  extern __shared__ __align__(16) unsigned char ms_smem[];
+  __shared__ float sh[LT / 32];
+  const int b = blockIdx.x;
+  const int nt = toff[b + 1] - toff[b], ns = exclude_seen ? len[b] : 0, S = nt + ns;
+  int32_t* sp_id = reinterpret_cast<int32_t*>(ms_smem);
+  float* sp_p = reinterpret_cast<float*>(sp_id + S);
+  float* row = pred + (int64_t)b * ld;
+  const float w0 = w_neg[b];
+  for (int i = threadIdx.x; i < S; i += LT) {
+    const int id = i < nt ? tids[toff[b] + i] : X[((int64_t)b * T + (i - nt)) * K];
+    sp_id[i] = id;
+    sp_p[i] = (id >= 0 && id < N) ? row[id] + bias[id] : 0.f;
+  }
+  __syncthreads();
+  float lpart = 0.f;
+  for (int n = threadIdx.x; n < N; n += LT) {
+    float l, d;
+    margin_elem(loss, row[n] + bias[n], def_tgt ? def_tgt[n] : 0.f, w0, l, d);
+    lpart += l;
+    row[n] = d * inv_gb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += LT) {
+    const int id = sp_id[i];
+    if (id < 0 || id >= N) continue;
+    bool last = true;
+    for (int j = i + 1; j < S && last; ++j) last = sp_id[j] != id;
+    if (!last) continue;
+    float l0, d0, l1, d1;
+    margin_elem(loss, sp_p[i], def_tgt ? def_tgt[id] : 0.f, w0, l0, d0);
+    if (i < nt) margin_elem(loss, sp_p[i], 1.f, -1.f, l1, d1);
+    else margin_elem(loss, sp_p[i], 0.f, 0.f, l1, d1);
+    lpart += l1 - l0;
+    row[id] = d1 * inv_gb;
+  }
+  const float l = block_sum(lpart, sh);
+  if (threadIdx.x == 0) row_loss[b] = l * inv_gb;
+}
+
 // weight[b,:] = w_neg[b] ; Y[b,:] = default ; then targets (Y=1, w=-1)
 __global__ void margin_fill_kernel(float* __restrict__ Y, float* __restrict__ W, const int32_t* __restrict__ toff,
                                    const int32_t* __restrict__ tids, const float* __restrict__ w_neg,
@@ -360,6 +428,24 @@ int launch_margin_loss(sbr_model* m, int loss, float* pred, int ld, const float*
                        const float* W, int B, int N, float inv_gb, float* row_loss) {
   if (B == 0) return 0;
   margin_loss_kernel<<<B, LT, 0, m->stream>>>(loss, pred, ld, bias, Y, W, N, inv_gb, row_loss);
+  KERNEL_CHECK(m);
+  return 0;
+}
+
+int launch_margin_loss_ragged(sbr_model* m, int loss, float* pred, int ld, const float* bias, const int32_t* toff,
+                              const int32_t* tids, const int32_t* X, const int32_t* len, const float* w_neg,
+                              const float* def_tgt, int exclude_seen, int B, int T, int K, int N, int max_special,
+                              float inv_gb, float* row_loss) {
+  if (B == 0) return 0;
+  const size_t smem = (size_t)std::max(1, max_special) * 8;
+  if (smem > 200 * 1024) { sbr_set_error(m, SBR_E_ARG, "margin step: %d targets + seen items in one row", max_special); return SBR_E_ARG; }
+  static std::vector<int> attr_devs;
+  if (smem > 48 * 1024 && std::find(attr_devs.begin(), attr_devs.end(), m->dev) == attr_devs.end()) {
+    cudaFuncSetAttribute(margin_loss_ragged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_devs.push_back(m->dev);
+  }
+  margin_loss_ragged_kernel<<<B, LT, smem, m->stream>>>(loss, pred, ld, bias, toff, tids, X, len, w_neg, def_tgt, exclude_seen,
+                                                        T, K, N, inv_gb, row_loss);
   KERNEL_CHECK(m);
   return 0;
 }

@@ -54,6 +54,12 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  // optional (NCCL >= 2.19): user-buffer registration, so that the gradient arena is all-reduced in place through
+  // NVLink SHARP / NVLS instead of being staged through NCCL's internal buffers
+  ncclResult_t (*MemAlloc)(void**, size_t) = nullptr;
+  ncclResult_t (*MemFree)(void*) = nullptr;
+  ncclResult_t (*CommRegister)(const ncclComm_t, void*, size_t, void**) = nullptr;
+  ncclResult_t (*CommDeregister)(const ncclComm_t, void*) = nullptr;
 };
 NcclApi g_nccl;
 
@@ -73,6 +79,10 @@ bool load_nccl(std::string* why) {
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+  g_nccl.MemAlloc = (decltype(g_nccl.MemAlloc))dlsym(g_nccl.lib, "ncclMemAlloc");
+  g_nccl.MemFree = (decltype(g_nccl.MemFree))dlsym(g_nccl.lib, "ncclMemFree");
+  g_nccl.CommRegister = (decltype(g_nccl.CommRegister))dlsym(g_nccl.lib, "ncclCommRegister");
+  g_nccl.CommDeregister = (decltype(g_nccl.CommDeregister))dlsym(g_nccl.lib, "ncclCommDeregister");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
     *why = "libnccl.so.2 lacks a required symbol";
     g_nccl.lib = nullptr;
@@ -82,6 +92,17 @@ bool load_nccl(std::string* why) {
 }
 
 const char* kStageNames[SBR_N_STAGES] = {"h2d", "gather", "rnn_fwd", "output", "rnn_bwd", "wgrad", "scatter", "allreduce", "optimizer"};
+
+// X[b, t, :] = ids[(off[seq_b] + start_b + t), :] for t < len_b (0 beyond), lengths alongside
+__global__ void assemble_rows_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ ids, const int32_t* __restrict__ rows,
+                                     int32_t* __restrict__ X, int32_t* __restrict__ len, int B, int T, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T * K) return;
+  const int k = (int)(i % K), t = (int)((i / K) % T), b = (int)(i / ((int64_t)K * T));
+  const int s = rows[b], st = rows[B + b], l = rows[2 * B + b];
+  X[i] = t < l ? ids[((int64_t)off[s] + st + t) * K + k] : 0;
+  if (t == 0 && k == 0) len[b] = l;
+}
 
 __global__ void fill_rows_kernel(float* __restrict__ out, const float* __restrict__ bias, int64_t rows, int cols) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,12 +236,14 @@ extern "C" void sbr_destroy(sbr_model* m) {
   if (!m) return;
   cudaSetDevice(m->dev);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->nccl_comm && m->nccl_reg_handle && g_nccl.CommDeregister) g_nccl.CommDeregister((ncclComm_t)m->nccl_comm, m->nccl_reg_handle);
   if (m->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)m->nccl_comm);
   auto F = [](void* p) { if (p) cudaFree(p); };
+  if (m->grads_from_nccl && g_nccl.MemFree) { g_nccl.MemFree(m->grads); m->grads = nullptr; }
   F(m->params); F(m->grads); F(m->opt_a); F(m->opt_b);
   for (LayerDesc& L : m->layers) { F(L.Xg); F(L.act); F(L.hs); F(L.cs); F(L.dXg); F(L.dac); F(L.dhs); F(L.hT); F(L.aT); }
   for (BatchSlot& s : m->slots) { F(s.X); F(s.len); F(s.Y); F(s.pop); }
-  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe); F(m->scan_sync);
+  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe); F(m->scan_sync); F(m->ds_off); F(m->ds_ids); F(m->ds_rows);
   F(m->mY); F(m->mW); F(m->cells); F(m->Wc); F(m->dWc); F(m->bc);
   F(m->tgt_off); F(m->tgt_ids); F(m->w_neg); F(m->def_tgt); F(m->excl_off); F(m->excl_ids); F(m->topk_ids);
   if (m->h_len) cudaFreeHost(m->h_len);
@@ -254,6 +277,8 @@ static int create_impl(sbr_model* m) {
   m->use_step_scan = getenv("SBR_DISABLE_STEP_SCAN") == nullptr;
   m->use_tma_gemm = getenv("SBR_DISABLE_TMA_GEMM") == nullptr;
   m->use_persistent_scan = getenv("SBR_DISABLE_PERSISTENT_SCAN") == nullptr;
+  if (const char* e = getenv("SBR_SCAN_FENCE")) m->scan_fence_mode = atoi(e);
+  m->use_splitk_scan = getenv("SBR_DISABLE_SPLITK_SCAN") == nullptr;
   m->no_side_stream = getenv("SBR_NO_SIDE_STREAM") != nullptr;
   m->no_early_cost = getenv("SBR_NO_EARLY_COST") != nullptr;
   m->disable_tc = getenv("SBR_DISABLE_TC") != nullptr;
@@ -280,7 +305,19 @@ static int create_impl(sbr_model* m) {
   const size_t arena = (size_t)m->P_pad + 4;
   int rc;
   if ((rc = dev_alloc(m, &m->params, arena))) return rc;
-  if ((rc = dev_alloc(m, &m->grads, arena))) return rc;
+  if (c.n_ranks > 1 && !getenv("SBR_NO_NCCL_REGISTER")) {
+    // the all-reduced buffer comes from NCCL's allocator and is registered with the communicator below
+    std::string why;
+    if (load_nccl(&why) && g_nccl.MemAlloc && g_nccl.MemFree && g_nccl.CommRegister) {
+      void* p = nullptr;
+      if (g_nccl.MemAlloc(&p, arena * sizeof(float)) == ncclSuccess && p) {
+        m->grads = static_cast<float*>(p);
+        m->grads_from_nccl = true;
+        CU_TRY(m, cudaMemset(m->grads, 0, arena * sizeof(float)));
+      }
+    }
+  }
+  if (!m->grads && (rc = dev_alloc(m, &m->grads, arena))) return rc;
   if ((rc = dev_alloc(m, &m->opt_a, arena))) return rc;
   const bool two = c.updater == SBR_UPD_ADAM || c.updater == SBR_UPD_ADADELTA;
   if ((rc = dev_alloc(m, &m->opt_b, two ? arena : 4))) return rc;
@@ -337,8 +374,8 @@ static int create_impl(sbr_model* m) {
     if ((rc = dev_alloc(m, &m->bc, 2 * n_cells))) return rc;
   }
   if (margin) {
-    if ((rc = dev_alloc(m, &m->mY, B * m->N))) return rc;
-    if ((rc = dev_alloc(m, &m->mW, B * m->N))) return rc;
+    // the dense [B, n_items] target / weight matrices of the reference exist only for callers of the dense entry point
+    // (sbr_train_step_margin_dense allocates them on first use); the ragged entry point never materialises them
     if ((rc = dev_alloc(m, &m->tgt_off, B + 1))) return rc;
     if ((rc = dev_alloc(m, &m->w_neg, B))) return rc;
     if ((rc = dev_alloc(m, &m->def_tgt, m->N))) return rc;
@@ -375,6 +412,10 @@ static int create_impl(sbr_model* m) {
       return SBR_E_NCCL;
     }
     m->nccl_comm = comm;
+    if (m->grads_from_nccl) {
+      void* handle = nullptr;
+      if (g_nccl.CommRegister(comm, m->grads, ((size_t)m->P_pad + 4) * sizeof(float), &handle) == ncclSuccess) m->nccl_reg_handle = handle;
+    }
   }
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   CU_TRY(m, cudaDeviceSynchronize());
@@ -576,6 +617,75 @@ static int stage_cce_impl(sbr_model* m, int slot, const int32_t* X, const float*
     m->staging_in_flight = false;
   }
   return 0;
+}
+
+static int begin_step(sbr_model* m);
+static int step_cce(sbr_model* m, const BatchSlot& s, float* cost);
+
+extern "C" int sbr_dataset_upload(sbr_model* m, int n_seqs, const int32_t* offsets, const int32_t* ids) {
+  CHECK_STICKY(m);
+  if (n_seqs < 1 || !offsets || !ids || offsets[0] != 0) { sbr_set_error(m, SBR_E_ARG, "dataset_upload: bad arguments"); return SBR_E_ARG; }
+  for (int i = 0; i < n_seqs; ++i)
+    if (offsets[i + 1] < offsets[i]) { sbr_set_error(m, SBR_E_ARG, "dataset_upload: offsets must be non-decreasing"); return SBR_E_ARG; }
+  const int64_t total = offsets[n_seqs];
+  for (int64_t i = 0; i < total * m->K; ++i)
+    if (ids[i] < 0 || ids[i] >= m->n_in) { sbr_set_error(m, SBR_E_RANGE, "dataset id %d outside [0,%d)", ids[i], m->n_in); return SBR_E_RANGE; }
+  CU_TRY(m, cudaSetDevice(m->dev));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  if (m->ds_off) cudaFree(m->ds_off);
+  if (m->ds_ids) cudaFree(m->ds_ids);
+  m->ds_off = m->ds_ids = nullptr;
+  int rc;
+  if ((rc = dev_alloc(m, &m->ds_off, (size_t)n_seqs + 1, false))) return rc;
+  if ((rc = dev_alloc(m, &m->ds_ids, (size_t)std::max<int64_t>(1, total * m->K), false))) return rc;
+  if (!m->ds_rows && (rc = dev_alloc(m, &m->ds_rows, (size_t)3 * m->B))) return rc;
+  CU_TRY(m, cudaMemcpyAsync(m->ds_off, offsets, ((size_t)n_seqs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+  if (total > 0) CU_TRY(m, cudaMemcpyAsync(m->ds_ids, ids, (size_t)total * m->K * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  m->ds_n = n_seqs;
+  m->ds_hoff.assign(offsets, offsets + n_seqs + 1);
+  return 0;
+}
+
+extern "C" int sbr_train_step_cce_rows(sbr_model* m, const int32_t* seq, const int32_t* start, const int32_t* len,
+                                       const int32_t* Y, const float* pop, int B, float* cost) {
+  CHECK_STICKY(m);
+  if (m->cfg.loss != SBR_LOSS_CCE) { sbr_set_error(m, SBR_E_ARG, "model was not created with the CCE loss"); return SBR_E_ARG; }
+  if (m->ds_n == 0) { sbr_set_error(m, SBR_E_ARG, "no dataset uploaded (sbr_dataset_upload)"); return SBR_E_ARG; }
+  if (!seq || !start || !len || !Y || !pop || B < 1 || B > m->B) { sbr_set_error(m, SBR_E_ARG, "train_step_cce_rows: bad arguments"); return SBR_E_ARG; }
+  int rc;
+  if ((rc = begin_step(m))) return rc;
+  stage_mark(m, 0);
+  if (m->staging_in_flight) {
+    CU_TRY(m, cudaEventSynchronize(m->ev_staged));
+    m->staging_in_flight = false;
+  }
+  BatchSlot& s = m->slots[0];
+  int32_t* h = static_cast<int32_t*>(m->h_stage);       // pinned: [3, B] triples (B*T*K*4 bytes available)
+  int t_max = 0;
+  for (int b = 0; b < B; ++b) {
+    const int sq = seq[b], st = start[b], l = len[b];
+    if (sq < 0 || sq >= m->ds_n || st < 0 || l < 0 || l > m->T || st + l > m->ds_hoff[sq + 1] - m->ds_hoff[sq]) {
+      sbr_set_error(m, SBR_E_RANGE, "row %d: (sequence %d, start %d, length %d) outside the uploaded dataset / max_length %d", b, sq, st, l, m->T);
+      return SBR_E_RANGE;
+    }
+    if (Y[b] < 0 || Y[b] >= m->N) { sbr_set_error(m, SBR_E_RANGE, "Y[%d] = %d outside [0,%d)", b, Y[b], m->N); return SBR_E_RANGE; }
+    h[b] = sq; h[B + b] = st; h[2 * B + b] = l;
+    m->h_len[b] = l;
+    t_max = std::max(t_max, l);
+  }
+  s.B = B; s.t_max = t_max; s.n_all = B; s.row_offset = 0;
+  s.hlen.assign(m->h_len, m->h_len + B);
+  CU_TRY(m, cudaMemcpyAsync(m->ds_rows, h, (size_t)3 * B * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(s.Y, Y, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(s.pop, pop, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaEventRecord(m->ev_staged, m->stream));
+  m->staging_in_flight = true;
+  const int64_t n = (int64_t)B * m->T * m->K;
+  assemble_rows_kernel<<<cdiv(n, 256), 256, 0, m->stream>>>(m->ds_off, m->ds_ids, m->ds_rows, s.X, s.len, B, m->T, m->K);
+  KERNEL_CHECK(m);
+  float local_cost;
+  return step_cce(m, s, cost ? cost : &local_cost);
 }
 
 extern "C" int sbr_stage_cce(sbr_model* m, int slot, const int32_t* X, const float* mask, const int32_t* Y,
@@ -889,13 +999,19 @@ extern "C" int sbr_train_step_sampled(sbr_model* m, const int32_t* X, const floa
   return finish_step(m, cost);
 }
 
-static int step_margin(sbr_model* m, const BatchSlot& s, float* cost) {
+struct MarginRagged { bool on = false; bool has_default = false; int exclude_seen = 0; int max_special = 0; };
+
+static int step_margin(sbr_model* m, const BatchSlot& s, float* cost, const MarginRagged& rg = MarginRagged()) {
   int rc;
   const float inv_gb = 1.f / (float)(m->cfg.global_batch > 0 ? m->cfg.global_batch : s.B * m->cfg.n_ranks);
   if ((rc = forward_stack(m, s))) return rc;
   const int B = s.B, N = m->N, H = m->H_last;
   if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, N, 1.f, 0.f))) return rc;
-  if ((rc = launch_margin_loss(m, m->cfg.loss, m->logits, N, m->params + m->out_b, m->mY, m->mW, B, N, inv_gb, m->row_loss))) return rc;
+  if (rg.on) {
+    if ((rc = launch_margin_loss_ragged(m, m->cfg.loss, m->logits, N, m->params + m->out_b, m->tgt_off, m->tgt_ids, s.X, s.len, m->w_neg,
+                                        rg.has_default ? m->def_tgt : nullptr, rg.exclude_seen, B, m->T, m->K, N, rg.max_special, inv_gb,
+                                        m->row_loss))) return rc;
+  } else if ((rc = launch_margin_loss(m, m->cfg.loss, m->logits, N, m->params + m->out_b, m->mY, m->mW, B, N, inv_gb, m->row_loss))) return rc;
   if ((rc = launch_reduce_cost(m, m->row_loss, B, m->grads + m->cost_slot))) return rc;
   if ((rc = output_backward_full(m, B))) return rc;
   stage_mark(m, 4);
@@ -913,6 +1029,10 @@ extern "C" int sbr_train_step_margin_dense(sbr_model* m, const int32_t* X, const
   stage_mark(m, 0);
   BatchSlot& s = m->slots[0];
   if ((rc = stage_common(m, s, X, mask, B))) return rc;
+  if (!m->mY) {
+    if ((rc = dev_alloc(m, &m->mY, (size_t)m->B * m->N, false))) return rc;
+    if ((rc = dev_alloc(m, &m->mW, (size_t)m->B * m->N, false))) return rc;
+  }
   CU_TRY(m, cudaMemcpyAsync(m->mY, Ymat, (size_t)B * m->N * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaMemcpyAsync(m->mW, weight, (size_t)B * m->N * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
@@ -945,9 +1065,11 @@ extern "C" int sbr_train_step_margin(sbr_model* m, const int32_t* X, const float
   CU_TRY(m, cudaMemcpyAsync(m->w_neg, w_neg, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   if (default_target) CU_TRY(m, cudaMemcpyAsync(m->def_tgt, default_target, (size_t)m->N * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
-  if ((rc = launch_margin_fill(m, m->mY, m->mW, s.X, s.len, m->tgt_off, m->tgt_ids, m->w_neg,
-                               default_target ? m->def_tgt : nullptr, exclude_seen, B, m->T, m->K, m->N))) return rc;
-  return step_margin(m, s, cost);
+  MarginRagged rg;
+  rg.on = true; rg.has_default = default_target != nullptr; rg.exclude_seen = exclude_seen;
+  for (int b = 0; b < B; ++b)
+    rg.max_special = std::max(rg.max_special, target_offsets[b + 1] - target_offsets[b] + (exclude_seen ? m->h_len[b] : 0));
+  return step_margin(m, s, cost, rg);
 }
 
 // ------------------------------------------------------------------------------------------------

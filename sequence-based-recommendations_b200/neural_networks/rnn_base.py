@@ -102,11 +102,24 @@ class threaded_generator(object):
         self.close()
 
 
+class CompactBatch(object):
+    """A training mini-batch in the device-assembly form: one (sequence index, start, length)
+    triple per row into the sequences uploaded once with Engine.dataset_upload, plus the per-row targets.  The
+    padded X / mask of the reference batch (rnn_one_hot.py:90-101) are built on the device from it."""
+    __slots__ = ("seq", "start", "length", "Y", "pop")
+
+    def __init__(self, seq, start, length, Y, pop):
+        self.seq, self.start, self.length, self.Y, self.pop = seq, start, length, Y, pop
+
+    def __len__(self):
+        return len(self.seq)
+
+
 class RNNBase(object):
     def __init__(self, sequence_noise=None, recurrent_layer=None, updater=None, target_selection=None,
                  interactions_are_unique=True, other_features=None, use_ratings_features=True, movies_features=None,
                  use_movies_features=True, users_features=None, use_users_features=True, max_length=MAX_LENGTH,
-                 batch_size=BATCH_SIZE, device=0, n_ranks=1, rank=0, nccl_id=None, prefetch_batches=0, init_seed=None, control=None):
+                 batch_size=BATCH_SIZE, device=0, n_ranks=1, rank=0, nccl_id=None, prefetch_batches=0, init_seed=None, control=None, device_batches=True):
         self.sequence_noise = sequence_noise if sequence_noise is not None else SequenceNoise()
         self.recurrent_layer = recurrent_layer if recurrent_layer is not None else RecurrentLayers()
         self.updater = updater if updater is not None else Adagrad()
@@ -125,6 +138,10 @@ class RNNBase(object):
         self.init_seed = init_seed
         # multi-rank control plane (helpers/rendezvous.Control) or None; used to make wall-clock decisions collective
         self.control = control
+        # build the padded mini-batch tensors on the device from (sequence, start, length) triples when the model
+        # supports it (RNNOneHot; no sequence noise: the uploaded sequences must be the ones the rows are cut from)
+        self.device_batches = bool(device_batches)
+        self._uploaded = None       # user id -> index of its sequence in the uploaded CSR
         if batch_size % n_ranks != 0:
             raise ValueError("batch_size (%d) must be a multiple of the number of ranks (%d)" % (batch_size, n_ranks))
         self.local_batch = batch_size // n_ranks
@@ -316,6 +333,9 @@ class RNNBase(object):
         if load_last_model:
             epochs_offset = self.load_last(save_dir)
 
+        if (self.device_batches and self._supports_device_batches and self.sequence_noise.name == ""
+                and self._uploaded is None and dataset.training_set.lines):
+            self._upload_training_sequences(dataset)
         batch_generator = self._gen_mini_batch(self.sequence_noise(dataset.training_set()))
         if self.prefetch_batches > 0 and not getattr(self.target_selection, 'determinist_test', True):
             raise ValueError("--prefetch and --rand_test_target draw from the same RNG streams in two threads; "
@@ -428,11 +448,64 @@ class RNNBase(object):
         metrics['blockbuster_share'].append(ev.blockbuster_share())
         return metrics
 
+    _supports_device_batches = False
+
+    def _upload_training_sequences(self, dataset):
+        """Encode every training sequence once ([L, K] ids) and hand the CSR to the library."""
+        lines = dataset.training_set.lines
+        feats = [self._features_of(seq) for _, seq in lines]
+        off = np.zeros(len(lines) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(f) for f in feats])
+        if off[-1] >= 2 ** 31:
+            return False
+        ids = np.concatenate(feats, axis=0) if feats else np.zeros((0, self._input_size()), np.int32)
+        self.engine.dataset_upload(off.astype(np.int32), ids)
+        self._uploaded = {uid: i for i, (uid, _) in enumerate(lines)}
+        return True
+
+    def _plain_first_target(self):
+        """True when a row's target is simply the item that follows its input window: one target, no shuffling, no
+        popularity-biased skipping (target_selection.py:41-53 then draws nothing from the RNGs)."""
+        ts = self.target_selection
+        return (type(ts) is SelectTargets and ts.n_targets == 1 and not ts.shuffle and ts.bias < 0
+                and hasattr(self, '_compact_from_triples'))
+
+    def _gen_compact_batches(self, sequence_generator, max_reuse_sequence=np.inf):
+        """_gen_mini_batch for the device-assembly form, one numpy pass per USER instead of one python iteration per
+        ROW: the same `random.sample` calls in the same order as the row loop below (so the rows, and a seeded run,
+        are identical), but the windows / targets of a user's rows are cut with array arithmetic.  With several ranks
+        every process still walks the same global batch, now at a cost that does not grow with the row count."""
+        T, Bsz = self.max_length, self.batch_size
+        while True:
+            j = 0
+            seq_idx, starts, lens, ys = [], [], [], []
+            while j < Bsz:
+                try:
+                    sequence, user_id = next(sequence_generator)
+                except StopIteration:
+                    return
+                n_pick = int(min([Bsz - j, len(sequence) - 2, max_reuse_sequence]))
+                if n_pick <= 0:
+                    continue
+                ls = np.array(sorted(random.sample(range(2, len(sequence)), n_pick)), dtype=np.int64)
+                st = np.maximum(0, ls - T)
+                seq_idx.append(np.full(n_pick, self._uploaded[user_id], dtype=np.int32))
+                starts.append(st)
+                lens.append(ls - st)
+                ys.append(sequence[ls, 0])
+                j += n_pick
+            yield self._compact_from_triples(np.concatenate(seq_idx), np.concatenate(starts).astype(np.int32),
+                                             np.concatenate(lens).astype(np.int32),
+                                             np.concatenate(ys).astype(np.int32))
+
     def _gen_mini_batch(self, sequence_generator, test=False, max_reuse_sequence=np.inf):
         """Mini-batch generator with the reference's semantics (rnn_base.py:373-420): a training batch
         is made of nested prefixes -- sorted random split points l in [2, len) of as few user
         sequences as needed to fill exactly batch_size rows; row = (user, seq[max(0,l-T):l],
         targets chosen in seq[l:]).  test=True: one row per user, split in the middle."""
+        if not test and self._uploaded is not None and self._plain_first_target():
+            yield from self._gen_compact_batches(sequence_generator, max_reuse_sequence)
+            return
         while True:
             j = 0
             sequences = []
@@ -458,7 +531,10 @@ class RNNBase(object):
                         continue
                     start = max(0, l - self.max_length)
                     row = [user_id, sequence[start:l], target]
-                    if ids is not None:
+                    if not test and self._uploaded is not None:
+                        row.append(None)
+                        row.append((self._uploaded[user_id], start, l - start))     # device-assembly triple
+                    elif ids is not None:
                         row.append(ids[start:l])
                     sequences.append(row)
                 j += len(seq_lengths) - skipped_seq
@@ -482,7 +558,7 @@ class RNNBase(object):
         for i, row in enumerate(sequences):
             in_seq = row[1]
             n = len(in_seq)
-            X[i, :n, :] = row[3] if len(row) > 3 else self._features_of(in_seq)   # pre-encoded view, see _gen_mini_batch
+            X[i, :n, :] = row[3] if (len(row) > 3 and row[3] is not None) else self._features_of(in_seq)   # pre-encoded view
             lens[i] = n
             seen.append(X[i, :n, 0])
         mask = (np.arange(self.max_length)[None, :] < lens[:, None]).astype(np.float32)

@@ -21,13 +21,23 @@ class RNNOneHot(rnn.RNNBase):
     def _engine_extra_kwargs(self):
         return dict(regularization=float(self.regularization))
 
+    _supports_device_batches = True
+
     def _compile_train_function(self):
         """train_function(X, mask, Y, pop, exclude) -> cost (rnn_one_hot.py:61, rnn_base.py:185).
-        `exclude` is accepted and ignored, as in the reference (on_unused_input='ignore')."""
-        def train_function(X, mask, Y, pop, exclude=None):
+        `exclude` is accepted and ignored, as in the reference (on_unused_input='ignore').  A CompactBatch (rows as
+        (sequence, start, length) triples of the uploaded training set) takes the device-assembly entry point; every
+        rank sends only its own rows."""
+        def train_function(X, mask=None, Y=None, pop=None, exclude=None):
             sl = self._split_rows
+            if isinstance(X, rnn.CompactBatch):
+                return self.engine.train_step_cce_rows(sl(X.seq), sl(X.start), sl(X.length), sl(X.Y), sl(X.pop))
             return self.engine.train_step_cce(sl(X), sl(mask), sl(Y), sl(pop))
         self.train_function = train_function
+
+    def _compact_from_triples(self, seq, start, length, Y):
+        pop = np.power(self.dataset.item_popularity[Y], self.diversity_bias).astype(np.float32)
+        return (rnn.CompactBatch(seq, start, length, Y, pop),)
 
     def _split_rows(self, arr):
         """This rank's rows of a global-batch array: row r goes to rank r % n_ranks.  The batch builder emits rows in
@@ -41,7 +51,11 @@ class RNNOneHot(rnn.RNNBase):
     def _prepare_input(self, sequences):
         """(X, mask, Y, pop, exclude) for a list of [user_id, input_sequence, targets]
         (rnn_one_hot.py:83-106); `exclude` is the ragged list of seen ids instead of a dense [B,N]."""
-        X, mask, seen = self._fill_inputs(sequences)
         Y = np.array([int(t[2][0][0]) for t in sequences], dtype=np.int32)       # first and only target
         pop = np.power(self.dataset.item_popularity[Y], self.diversity_bias).astype(np.float32)
+        if sequences and all(len(r) > 4 for r in sequences):
+            # device assembly: nothing but three integers per row leaves the host
+            tri = np.array([r[4] for r in sequences], dtype=np.int32)
+            return (rnn.CompactBatch(tri[:, 0].copy(), tri[:, 1].copy(), tri[:, 2].copy(), Y, pop),)
+        X, mask, seen = self._fill_inputs(sequences)
         return (X, mask, Y, pop, seen)

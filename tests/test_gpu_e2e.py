@@ -222,3 +222,38 @@ def test_two_rank_nccl_matches_single_rank(tmp_path, loss):
         assert abs(r0[0][s] - float(c_ref)) < 1e-4
     for a, b in zip(v64, r0[1]):
         assert np.abs(a - b).max() < 2e-4
+
+
+def test_device_side_batch_assembly_gives_identical_training(dataset):
+    """rows sent as (sequence, start, length) triples and assembled on the device train exactly like the
+    reference-style X / mask batches (same RNG state -> same rows -> identical costs; parameters equal up to the order of the atomic gradient sums)."""
+    from sbr_b200.neural_networks.recurrent_layers import RecurrentLayers
+    from sbr_b200.neural_networks.rnn_one_hot import RNNOneHot
+    from sbr_b200.neural_networks.update_manager import Adam
+
+    def run(device_batches):
+        random.seed(5); np.random.seed(5)
+        p = RNNOneHot(recurrent_layer=RecurrentLayers(layer_type="GRU", layers=[48]), updater=Adam(), max_length=20, batch_size=16,
+                      use_ratings_features=True, use_movies_features=False, use_users_features=False, init_seed=3,
+                      device_batches=device_batches)
+        p.prepare_model(dataset)
+        p.set_dataset(dataset)
+        p._compile_train_function()
+        if device_batches:
+            assert p._upload_training_sequences(dataset)
+        gen = p._gen_mini_batch(dataset.training_set())
+        costs = []
+        for _ in range(12):
+            batch = next(gen)
+            if device_batches:
+                assert len(batch) == 1
+            costs.append(float(p.train_function(*batch)))
+        vals = p.engine.get_all_param_values()
+        p.engine.close()
+        return costs, vals
+
+    c_rows, v_rows = run(True)
+    c_dense, v_dense = run(False)
+    assert c_rows == c_dense
+    for a, b in zip(v_rows, v_dense):       # gradient sums are accumulated with floating-point atomics: equal up to their order
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-6)

@@ -109,13 +109,15 @@ def test_ffma_and_tensor_core_engines_agree(eng):
 @pytest.mark.parametrize("cell,layers,B,T", [("LSTM", (256,), 160, 7), ("GRU", (512,), 130, 6), ("LSTM", (256, 256), 140, 6),
                                              ("GRU", (512, 512), 256, 5), ("Vanilla", (320,), 40, 6), ("LSTM", (512,), 33, 5),
                                              ("GRU", (240,), 64, 6)])
-@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("persistent", [True, "no-split-k", False])
 def test_step_scans_match_oracle(cell, layers, B, T, persistent, monkeypatch):
     """H > 224 (H % 16 == 0): the persistent cooperative tensor-core scans (tc_scan.cu, one launch per layer), or with
     SBR_DISABLE_PERSISTENT_SCAN one tcgen05 step kernel per time step (tc_gemm.cu); forward and BPTT; batch sizes that
     are not multiples of the 128-row / 32-column tiles."""
     if not persistent:
         monkeypatch.setenv("SBR_DISABLE_PERSISTENT_SCAN", "1")
+    elif persistent == "no-split-k":
+        monkeypatch.setenv("SBR_DISABLE_SPLITK_SCAN", "1")      # BPTT: one CTA per tile instead of a split-K cluster of 4
     spec = O.Spec(n_items=173, cell=cell, layers=layers, loss="CCE")
     check_grads(spec, B=B, T=T, seed=len(layers) + B)
 

@@ -267,3 +267,69 @@ def test_pre_encoded_rows_give_the_same_batches(rf, tmp_path):
             assert out[0].dtype == np.int32 and out[1].dtype == np.float32
             lens = out[1].sum(1).astype(int)
             assert ((out[1] == 1) == (np.arange(12)[None, :] < lens[:, None])).all()
+
+
+@pytest.mark.parametrize("rf", [False, True])
+def test_compact_batches_describe_the_same_rows(rf, dataset):
+    """Device-side assembly: with the training sequences uploaded, a training batch is B (sequence,
+    start, length) triples; expanding them against the uploaded CSR gives exactly the X / mask / Y / pop of the
+    reference-style batch built from the same RNG state."""
+    class FakeEngine(object):
+        def dataset_upload(self, off, ids):
+            self.off, self.ids = np.asarray(off), np.asarray(ids)
+
+    p_dense = _pred(RNNOneHot, dataset, rf=rf)
+    p_rows = _pred(RNNOneHot, dataset, rf=rf)
+    assert p_rows._plain_first_target() or True
+    p_rows.engine = FakeEngine()
+    assert p_rows._upload_training_sequences(dataset)
+    eng = p_rows.engine
+    assert eng.ids.shape[1] == (2 if rf else 1) and eng.off[-1] == len(eng.ids)
+    random.seed(11); np.random.seed(11)
+    g_dense = p_dense._gen_mini_batch(dataset.training_set())
+    dense = [next(g_dense) for _ in range(4)]
+    random.seed(11); np.random.seed(11)
+    g_rows = p_rows._gen_mini_batch(dataset.training_set())
+    rows = [next(g_rows) for _ in range(4)]
+    from sbr_b200.neural_networks.rnn_base import CompactBatch
+    for (X, mask, Y, pop, seen), batch in zip(dense, rows):
+        assert len(batch) == 1 and isinstance(batch[0], CompactBatch)
+        cb = batch[0]
+        assert len(cb) == X.shape[0]
+        X2 = np.zeros_like(X)
+        for b in range(len(cb)):
+            lo = eng.off[cb.seq[b]] + cb.start[b]
+            X2[b, :cb.length[b]] = eng.ids[lo:lo + cb.length[b]]
+        np.testing.assert_array_equal(X2, X)
+        np.testing.assert_array_equal(cb.length, mask.sum(1).astype(np.int32))
+        np.testing.assert_array_equal(cb.Y, Y)
+        np.testing.assert_array_equal(cb.pop, pop)
+    # validation batches keep the reference form (they are not rows of the training set)
+    (Xv, maskv, *_), goal = next(p_rows._gen_mini_batch(dataset.validation_set(epochs=1), test=True))
+    assert Xv.shape[0] == 1 and maskv.sum() >= 1 and len(goal) >= 1
+
+
+def test_vectorised_and_row_loop_compact_generators_agree(dataset):
+    """The per-user numpy pass (`_gen_compact_batches`, used when a row's target is just the next item) and the row loop
+    of `_gen_mini_batch` consume the RNGs identically and produce the same triples / targets."""
+    class FakeEngine(object):
+        def dataset_upload(self, off, ids):
+            pass
+
+    from sbr_b200.neural_networks.rnn_base import CompactBatch
+    outs = []
+    for force_loop in (False, True):
+        p = _pred(RNNOneHot, dataset, B=32)
+        p.engine = FakeEngine()
+        assert p._upload_training_sequences(dataset)
+        if force_loop:
+            p._plain_first_target = lambda: False
+        else:
+            assert p._plain_first_target()
+        random.seed(21); np.random.seed(21)
+        g = p._gen_mini_batch(dataset.training_set())
+        outs.append([next(g)[0] for _ in range(6)])
+    for a, b in zip(*outs):
+        assert isinstance(a, CompactBatch) and isinstance(b, CompactBatch)
+        for f in ("seq", "start", "length", "Y", "pop"):
+            np.testing.assert_array_equal(getattr(a, f), getattr(b, f))

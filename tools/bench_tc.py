@@ -48,8 +48,14 @@ def scan():
     for name, cell, layers, B, T, N in [("c3 LSTM 2x256 B512 T200", "LSTM", (256, 256), 512, 200, 2000),
                                         ("c4-shard LSTM 1x512 B256 T200", "LSTM", (512,), 256, 200, 2000),
                                         ("c5-shard GRU 2x512 B256 T500", "GRU", (512, 512), 256, 500, 2000)]:
-        for env in ({}, {"SBR_DISABLE_STEP_SCAN": "1"}):
-            os.environ.pop("SBR_DISABLE_STEP_SCAN", None)
+        envs = [{}, {"SBR_DISABLE_STEP_SCAN": "1"}]
+        if len(sys.argv) > 2 and not any(name.startswith(c) for c in sys.argv[2].split(",")):
+            continue
+        if len(sys.argv) > 3:
+            envs = [dict(kv.split("=") for kv in e.split(",")) if e != "-" else {} for e in sys.argv[3:]]
+        for env in envs:
+            for k in ("SBR_DISABLE_STEP_SCAN", "SBR_SCAN_FENCE", "SBR_DISABLE_PERSISTENT_SCAN", "SBR_DISABLE_SPLITK_SCAN"):
+                os.environ.pop(k, None)
             os.environ.update(env)
             e = _capi.Engine(n_items=N, cell=cell, layers=layers, max_length=T, batch_size=B)
             vals = [rng.normal(0, 0.05, size=s).astype(np.float32) for _, s in e.param_infos()]
