@@ -172,6 +172,7 @@ struct sbr_model {
   bool use_tc_gemm = true;       // SBR_DISABLE_TC_GEMM: FFMA GEMMs everywhere
   bool use_step_scan = true;
   bool use_persistent_scan = true;   // SBR_DISABLE_PERSISTENT_SCAN: one launch per time step instead of the cooperative scans
+  bool use_scan_multicast = false; // SBR_SCAN_MULTICAST=1: clusters of 4 forward-scan CTAs share the h tile through TMA multicast (measured: no faster, the loads are not the limiter)
   bool use_splitk_scan = true;   // SBR_DISABLE_SPLITK_SCAN: one CTA per BPTT tile instead of a split-K cluster of 4
   int scan_fence_mode = 3;       // SBR_SCAN_FENCE: how the persistent scans publish a step (tc_scan.cu::publish_step)
   bool use_tma_gemm = true;      // SBR_DISABLE_TMA_GEMM: cp.async loaders in tc_gemm.cu even where a tensor map is possible

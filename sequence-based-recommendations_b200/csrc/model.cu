@@ -279,6 +279,7 @@ static int create_impl(sbr_model* m) {
   m->use_persistent_scan = getenv("SBR_DISABLE_PERSISTENT_SCAN") == nullptr;
   if (const char* e = getenv("SBR_SCAN_FENCE")) m->scan_fence_mode = atoi(e);
   m->use_splitk_scan = getenv("SBR_DISABLE_SPLITK_SCAN") == nullptr;
+  m->use_scan_multicast = getenv("SBR_SCAN_MULTICAST") != nullptr;
   m->no_side_stream = getenv("SBR_NO_SIDE_STREAM") != nullptr;
   m->no_early_cost = getenv("SBR_NO_EARLY_COST") != nullptr;
   m->disable_tc = getenv("SBR_DISABLE_TC") != nullptr;

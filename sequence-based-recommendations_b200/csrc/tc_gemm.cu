@@ -37,7 +37,10 @@ using namespace tcx;
 namespace {
 
 constexpr int TG_KC = 32;        // k per pipeline stage = 4 MMA k-steps
-constexpr int TG_STAGES = 3;      // converted-operand ring: TMEM slots of A (64 columns each) + shared-memory tiles of B
+#ifndef SBR_TG_STAGES
+#define SBR_TG_STAGES 3
+#endif
+constexpr int TG_STAGES = SBR_TG_STAGES;      // converted-operand ring: TMEM slots of A (64 columns each) + shared-memory tiles of B
 constexpr int TG_LOOK_MAX = 8;    // raw fp32 ring: up to this many 32-wide k chunks in flight (args.look, sized by the shared-memory budget)
 constexpr int TG_NT = 544;       // warps 0-3: A converters + epilogue, 4-7: B converters, 8: MMA issuer, 9-12: A loaders, 13-16: B loaders
 constexpr int TG_A0 = 256;       // first TMEM column of the A ring (D1 | D2 occupy 2*BN <= 256 columns)
@@ -282,14 +285,15 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
         TG_ACC(w_full);
         const uint32_t sb = smem_u32(tg_base + (size_t)s * stage_bytes);
         const uint32_t ta = tA + (uint32_t)s * 64u;
+        uint64_t bhi = make_desc(sb, lbo, 128), blo = make_desc(sb + part_bytes, lbo, 128);
+        const uint64_t adv = (uint64_t)((2u * lbo) >> 4);      // two core matrices along K, in the descriptor's 16-byte units
 #pragma unroll
         for (int ks = 0; ks < TG_KC / 8; ++ks) {
-          const uint64_t bhi = make_desc(sb + (uint32_t)ks * 2u * lbo, lbo, 128);
-          const uint64_t blo = make_desc(sb + part_bytes + (uint32_t)ks * 2u * lbo, lbo, 128);
           mma_ts(tD1, ta + 8 * ks, bhi, idesc, acc);
           mma_ts(tD2, ta + 8 * ks, blo, idesc, acc);
           mma_ts(tD2, ta + TG_KC + 8 * ks, bhi, idesc, 1);
           acc = 1;
+          bhi += adv; blo += adv;
         }
         umma_commit(&empty[s]);        // the stage (TMEM slot + shared-memory slot) is free once these MMAs have read it
         TG_ACC(w_issue);

@@ -24,7 +24,9 @@ using namespace tcx;
 namespace {
 
 constexpr int SC_KC = 32;          // k per chunk (4 MMA k-steps)
-constexpr int SC_ST = 3;           // converted-operand stages (TMEM slots of A; shared-memory slots of B in the backward)
+constexpr int SC_ST = 7;           // converted-operand stages (TMEM slots of A, 64 columns each: 64 + 7*64 = 512 columns; shared-memory
+                                   // slots of B in the backward).  Deep on purpose: a slot is only free again once the MMAs that read it
+                                   // have COMPLETED (tcgen05.commit), ~1.5k cycles after the converter filled it
 constexpr int SC_BN = 32;          // MMA N: forward 4 gates x 8 units, backward 32 batch rows
 constexpr int SC_U = 8;
 constexpr int SC_NT = 352;         // warps 0-3 A converters + epilogue, 4-7 B converters, 8 MMA, 9 A producer, 10 B producer
@@ -79,6 +81,30 @@ __device__ __forceinline__ void publish_step(int mode, int tid, uint64_t* tmem_e
   }
 }
 
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+               "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+               "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+               :: "r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+
 struct ScanBars {
   uint64_t rawA_full[SC_LOOK_MAX], rawA_empty[SC_LOOK_MAX];
   uint64_t rawB_full[SC_LOOKB], rawB_empty[SC_LOOKB];
@@ -132,14 +158,16 @@ __device__ __forceinline__ void convert_a_chunk(ScanBars& bars, const uint8_t* r
 
 __device__ __forceinline__ void issue_chunk_mmas(uint32_t tD1, uint32_t tD2, uint32_t ta, uint32_t sb, uint32_t idesc, uint32_t& acc) {
   constexpr uint32_t lbo = SC_BN * 16u, part = SC_BN * SC_KC * 4u;
+  // descriptors built once per chunk; a k-step advances the start-address field (16-byte units) by two core matrices
+  uint64_t bhi = make_desc(sb, lbo, 128), blo = make_desc(sb + part, lbo, 128);
+  constexpr uint64_t adv = (2u * lbo) >> 4;
 #pragma unroll
   for (int ks = 0; ks < SC_KC / 8; ++ks) {
-    const uint64_t bhi = make_desc(sb + (uint32_t)ks * 2u * lbo, lbo, 128);
-    const uint64_t blo = make_desc(sb + part + (uint32_t)ks * 2u * lbo, lbo, 128);
     mma_ts(tD1, ta + 8 * ks, bhi, idesc, acc);
     mma_ts(tD2, ta + 8 * ks, blo, idesc, acc);
     mma_ts(tD2, ta + SC_KC + 8 * ks, bhi, idesc, 1);
     acc = 1;
+    bhi += adv; blo += adv;
   }
 }
 
@@ -158,8 +186,15 @@ template <int G>
 __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_constant__ ScanArgs a) {
   extern __shared__ __align__(1024) uint8_t sc_smem[];
   __shared__ ScanBars bars;
+  __shared__ __align__(8) uint64_t slot_free[SC_LOOK_MAX];     // every CTA of the cluster has consumed the raw A slot
   __shared__ uint32_t tmem_base_s;
   __shared__ int t_end_s;
+  // The CTAs of a cluster are consecutive unit slices of the SAME batch tile: they all need the same h_{t-1} tile, so
+  // each one fetches 128/CS of its rows per chunk and multicasts them into every CTA of the cluster (the tile leaves
+  // L2 once per cluster instead of once per CTA).
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
   uint8_t* const base = sc_smem + ((1024u - (smem_u32(sc_smem) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int u0 = blockIdx.x * SC_U, m0 = (blockIdx.y + a.tile0) * 128;
@@ -169,9 +204,14 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
   uint8_t* rawA0 = convB + (size_t)NC * stageB;                 // [LOOK][128][32] fp32
   uint8_t* rawB0 = rawA0 + (size_t)LOOK * (128 * SC_KC * 4);    // [SC_LOOKB][G][32 k][8 units] fp32
 
-  if (tid == 0) { t_end_s = 0; init_bars(bars, 4); }
+  if (tid == 0) {
+    t_end_s = 0;
+    init_bars(bars, 4);
+    for (int i = 0; i < SC_LOOK_MAX; ++i) mbar_init(&slot_free[i], CS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -183,6 +223,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
     atomicMax(&t_end_s, l);
   }
   __syncthreads();
+  if (CS > 1) cluster.sync();       // every CTA's barriers exist before any multicast / remote arrive
   const int t_end = t_end_s;
   const uint32_t tmem = tmem_base_s;
   const uint32_t tD1 = tmem, tD2 = tmem + SC_BN, tA = tmem + 64;
@@ -232,8 +273,8 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < 16; ++i) { pre[i] = d0[i] + w0[i]; pre[16 + i] = d1[i] + w1[i]; }
       }
+      float sv[4][8];
       if (active) {
-        float sv[4][8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if constexpr (G == 4) {
@@ -257,17 +298,20 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
             hreg[j] = tanh_fast(xg[0][j] + pre[j]);
           }
         }
-        const long long r1 = (long long)(t + 1) * B + b;
-        st8(a.hs + r1 * H + u0, hreg);
-        if (G == 4) st8(a.cs + r1 * H + u0, creg);
+        st8(a.hs + ((long long)(t + 1) * B + b) * H + u0, hreg);
+      }
+      SC_ACC(3);
+      // publish: the state block t+1 of this CTA's units is in global memory; the accumulators may be overwritten
+      publish_step(a.fence_mode, tid, &bars.tmem_empty, ctr);
+      // what only the backward pass reads (cell state, gate activations) is stored after the release: it does not
+      // have to drain before the other CTAs may start the next step
+      if (active) {
+        if (G == 4) st8(a.cs + ((long long)(t + 1) * B + b) * H + u0, creg);
         if (G > 1) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) st8(a.act + ((long long)t * B + b) * 4 * H + g * H + u0, sv[g]);
         }
       }
-      SC_ACC(3);
-      // publish: the state block t+1 of this CTA's units is in global memory; the accumulators may be overwritten
-      publish_step(a.fence_mode, tid, &bars.tmem_empty, ctr);
       SC_ACC(4);
     }
     if (tl) { for (int i = 0; i < 6; ++i) a.dbg[i] = ph[i]; a.dbg[6] = t_end; }
@@ -334,9 +378,23 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
         if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[8] += clock64() - w0;
         for (int c = 0; c < NC; ++c, ++gc) {
           const int rs = gc % LOOK;
-          if (gc >= LOOK) mbar_wait(&bars.rawA_empty[rs], ((gc / LOOK) - 1) & 1);
+          if (gc >= LOOK) {
+            mbar_wait(&bars.rawA_empty[rs], ((gc / LOOK) - 1) & 1);        // this CTA's converters are done with the slot
+            if (CS > 1) {
+              // tell every CTA of the cluster, then wait until all of them have told me: only then may anybody multicast into it
+              fence_acq_rel_cluster();
+              for (int q = 0; q < CS; ++q) mbar_arrive_remote_relaxed(map_to_rank(smem_u32(&slot_free[rs]), q));
+              mbar_wait_cluster(&slot_free[rs], ((gc / LOOK) - 1) & 1);
+            }
+          }
           mbar_arrive_expect_tx(&bars.rawA_full[rs], 128 * SC_KC * 4);
-          tma_load_2d(rawA0 + (size_t)rs * (128 * SC_KC * 4), &a.tmA, c * SC_KC, t * B + m0, &bars.rawA_full[rs]);
+          if (CS > 1) {
+            const int rows = 128 / CS;
+            tma_load_2d_multicast(rawA0 + (size_t)rs * (128 * SC_KC * 4) + (size_t)crank * rows * (SC_KC * 4), &a.tmA, c * SC_KC,
+                                  t * B + m0 + crank * rows, &bars.rawA_full[rs], (uint16_t)((1u << CS) - 1u));
+          } else {
+            tma_load_2d(rawA0 + (size_t)rs * (128 * SC_KC * 4), &a.tmA, c * SC_KC, t * B + m0, &bars.rawA_full[rs]);
+          }
         }
       }
     }
@@ -355,7 +413,8 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256));
+  if (CS > 1) cluster.sync();       // nobody leaves while a peer may still multicast into / arrive on this CTA
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 // ================================================================================================ backward
@@ -378,7 +437,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd_kernel(const __grid_cons
 
   if (tid == 0) { t_end_s = 0; init_bars(bars, 8); }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -609,7 +668,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd_kernel(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 // ================================================================================================ backward, split-K cluster
@@ -621,21 +680,6 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd_kernel(const __grid_cons
 // of rnn_tc.cu).  Every CTA then sums KS partials for ITS 32/KS batch rows and runs the gate-gradient epilogue for them.
 constexpr int SC_KS = 4;                     // cluster size along K
 constexpr int SC_OWN = SC_BN / SC_KS;        // batch rows owned by a CTA in the epilogue
-
-__device__ __forceinline__ uint32_t map_to_rank(uint32_t cta_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-               "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-               "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 template <int G>
 __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd2_kernel(const __grid_constant__ ScanArgs a) {
@@ -670,7 +714,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd2_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -952,7 +996,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd2_kernel(const __grid_con
   }
   tc_fence_before();
   cluster.sync();        // nobody leaves while a peer may still copy into this CTA's shared memory
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 __global__ void bcast_rows2_kernel(float* __restrict__ out, const float* __restrict__ v, int64_t rows, int cols) {
@@ -1014,7 +1058,7 @@ int launch_coop(sbr_model* m, Kern kern, dim3 grid, size_t smem, const ScanArgs&
 }
 
 template <typename Kern>
-int launch_cluster_coop(sbr_model* m, Kern kern, dim3 grid, int cluster_z, size_t smem, const ScanArgs& a) {
+int launch_cluster_coop(sbr_model* m, Kern kern, dim3 grid, dim3 cl, size_t smem, const ScanArgs& a) {
   static std::vector<std::pair<int, const void*>> attr_done;
   bool have = false;
   for (auto& kv : attr_done) have |= kv.first == m->dev && kv.second == (const void*)kern;
@@ -1027,7 +1071,7 @@ int launch_cluster_coop(sbr_model* m, Kern kern, dim3 grid, int cluster_z, size_
   cfg.gridDim = grid; cfg.blockDim = dim3(SC_NT, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = m->stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cluster_z;
+  attr[0].val.clusterDim.x = cl.x; attr[0].val.clusterDim.y = cl.y; attr[0].val.clusterDim.z = cl.z;
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 2;
@@ -1044,13 +1088,13 @@ int launch_cluster_coop(sbr_model* m, Kern kern, dim3 grid, int cluster_z, size_
 }
 
 template <typename Kern>
-int max_clusters(Kern kern, int cluster_z, size_t smem) {
+int max_clusters(Kern kern, dim3 cl, size_t smem) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(1, 1, cluster_z * 64); cfg.blockDim = dim3(SC_NT, 1, 1); cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(cl.x * 64, cl.y, cl.z); cfg.blockDim = dim3(SC_NT, 1, 1); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cluster_z;
+  attr[0].val.clusterDim.x = cl.x; attr[0].val.clusterDim.y = cl.y; attr[0].val.clusterDim.z = cl.z;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -1079,7 +1123,13 @@ int launch_rnn_forward_persistent(sbr_model* m, const LayerDesc& L, const int32_
   a.dbg = scan_dbg_buffer(m);
   a.B = B; a.H = H; a.G = G; a.t_max = t_max; a.n_chunks = cdiv(H, SC_KC);
   a.len = len; a.peep = m->params + L.peep; a.Xg = L.Xg; a.hs = L.hs; a.cs = L.cs; a.act = L.act;
-  if (!get_tmap(&a.tmA, L.hs, H, (uint64_t)(m->T + 1) * m->B, H, SC_KC, 128, true) ||
+  const int unit_ctas = cdiv(H, SC_U), n_tiles = cdiv(B, 128);
+  if (unit_ctas > m->n_sm) return 1;
+  // cluster of CS consecutive unit slices shares the h tile through TMA multicast
+  int CS = 1;
+  if (m->use_scan_multicast)
+    for (int c = 4; c >= 2; c >>= 1) if (unit_ctas % c == 0) { CS = c; break; }
+  if (!get_tmap(&a.tmA, L.hs, H, (uint64_t)(m->T + 1) * m->B, H, SC_KC, 128 / CS, true) ||
       !get_tmap(&a.tmB, m->params + L.W_hid, GH, H, GH, SC_U, SC_KC, false))
     return 1;
   const size_t fixed = (size_t)a.n_chunks * SC_BN * SC_KC * 8 + (size_t)SC_LOOKB * 4 * SC_KC * SC_U * 4 + 1024;
@@ -1088,9 +1138,13 @@ int launch_rnn_forward_persistent(sbr_model* m, const LayerDesc& L, const int32_
   const size_t smem = fixed + (size_t)a.look * 128 * SC_KC * 4;
   // batch tiles per launch: all CTAs of a launch must be co-resident (one per SM); rows are independent, so a larger
   // batch runs as several launches over slices of its tiles
-  const int unit_ctas = cdiv(H, SC_U), n_tiles = cdiv(B, 128);
-  const int tiles_per_launch = std::max(1, m->n_sm / unit_ctas);
-  if (unit_ctas > m->n_sm) return 1;
+  int tiles_per_launch = std::max(1, m->n_sm / unit_ctas);
+  if (CS > 1) {
+    static int slots[5] = {-1, -1, -1, -1, -1};
+    if (slots[CS] < 0) slots[CS] = max_clusters(tc_scan_fwd_kernel<4>, dim3(CS, 1, 1), smem);
+    tiles_per_launch = slots[CS] / (unit_ctas / CS);
+    if (tiles_per_launch < 1) { CS = 1; tiles_per_launch = std::max(1, m->n_sm / unit_ctas); get_tmap(&a.tmA, L.hs, H, (uint64_t)(m->T + 1) * m->B, H, SC_KC, 128, true); }
+  }
   CU_TRY(m, cudaMemsetAsync(m->scan_sync, 0, (size_t)std::max(n_tiles, cdiv(B, SC_BN)) * sizeof(unsigned int), m->stream));
   for (int t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
     const int nt = std::min(tiles_per_launch, n_tiles - t0);
@@ -1098,9 +1152,10 @@ int launch_rnn_forward_persistent(sbr_model* m, const LayerDesc& L, const int32_
     v.sync = m->scan_sync + t0;
     v.tile0 = t0;
     int rc;
-    if (G == 4) rc = launch_coop(m, tc_scan_fwd_kernel<4>, dim3(unit_ctas, nt, 1), smem, v);
-    else if (G == 3) rc = launch_coop(m, tc_scan_fwd_kernel<3>, dim3(unit_ctas, nt, 1), smem, v);
-    else rc = launch_coop(m, tc_scan_fwd_kernel<1>, dim3(unit_ctas, nt, 1), smem, v);
+    const dim3 grid(unit_ctas, nt, 1), cl(CS, 1, 1);
+    if (G == 4) rc = launch_cluster_coop(m, tc_scan_fwd_kernel<4>, grid, cl, smem, v);
+    else if (G == 3) rc = launch_cluster_coop(m, tc_scan_fwd_kernel<3>, grid, cl, smem, v);
+    else rc = launch_cluster_coop(m, tc_scan_fwd_kernel<1>, grid, cl, smem, v);
     if (rc) return rc;
   }
   if (h_last) {
@@ -1134,7 +1189,7 @@ int launch_rnn_backward_persistent(sbr_model* m, const LayerDesc& L, const int32
     v.look = (int)std::min<size_t>(SC_LOOK_MAX, (SC_SMEM_MAX - fixed2) / (128 * SC_KC * 4));
     const size_t smem2 = fixed2 + (size_t)v.look * 128 * SC_KC * 4;
     static int slots = -1;
-    if (slots < 0) slots = max_clusters(tc_scan_bwd2_kernel<4>, SC_KS, smem2);
+    if (slots < 0) slots = max_clusters(tc_scan_bwd2_kernel<4>, dim3(1, 1, SC_KS), smem2);
     const int tiles_per = slots / m_ctas0;      // batch tiles whose clusters are all co-resident
     if (tiles_per >= 1) {
       CU_TRY(m, cudaMemsetAsync(m->scan_sync, 0, (size_t)std::max(n_tiles0, cdiv(B, 128)) * sizeof(unsigned int), m->stream));
@@ -1143,9 +1198,9 @@ int launch_rnn_backward_persistent(sbr_model* m, const LayerDesc& L, const int32
         v.sync = m->scan_sync + t0;
         v.tile0 = t0;
         int rc;
-        if (G == 4) rc = launch_cluster_coop(m, tc_scan_bwd2_kernel<4>, dim3(nt, m_ctas0, SC_KS), SC_KS, smem2, v);
-        else if (G == 3) rc = launch_cluster_coop(m, tc_scan_bwd2_kernel<3>, dim3(nt, m_ctas0, SC_KS), SC_KS, smem2, v);
-        else rc = launch_cluster_coop(m, tc_scan_bwd2_kernel<1>, dim3(nt, m_ctas0, SC_KS), SC_KS, smem2, v);
+        if (G == 4) rc = launch_cluster_coop(m, tc_scan_bwd2_kernel<4>, dim3(nt, m_ctas0, SC_KS), dim3(1, 1, SC_KS), smem2, v);
+        else if (G == 3) rc = launch_cluster_coop(m, tc_scan_bwd2_kernel<3>, dim3(nt, m_ctas0, SC_KS), dim3(1, 1, SC_KS), smem2, v);
+        else rc = launch_cluster_coop(m, tc_scan_bwd2_kernel<1>, dim3(nt, m_ctas0, SC_KS), dim3(1, 1, SC_KS), smem2, v);
         if (rc) return rc;
       }
       scan_dbg_print(m, "split-K");

@@ -201,8 +201,8 @@ class RNNBase(object):
             elif leaf.startswith("W_"):
                 v = rng.normal(0.0, 0.1, size=shape)
             else:
-                v = np.zeros(shape)
-            vals.append(np.asarray(v, dtype=np.float32))
+                v = np.zeros(shape, dtype=np.float32)
+            vals.append(np.asarray(v, dtype=np.float32))     # drawn in float64 like Lasagne, stored as floatX
         self.engine.set_all_param_values(vals)
 
     def _common_filename(self, epochs):
