@@ -385,7 +385,9 @@ def main():
     eng.synchronize()
     # estimate a repetition, then repeat the K timed steps until the timed region is long enough for the clock sampler
     eng.timer_start()
+    t_enq = time.perf_counter()
     run_steps(W, W + K)
+    host_enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / K     # host time to enqueue a step, launch queue not yet full
     est_ms = max_over_ranks(eng.timer_stop())
     R = max(1, int(np.ceil(args.min_timed_s * 1e3 / max(est_ms, 1e-3))))
     R = int(max_over_ranks(R))
@@ -396,10 +398,8 @@ def main():
     barrier()
     launches0 = eng.kernel_launches()
     eng.timer_start()
-    t_enq = time.perf_counter()
     for _ in range(R):
         run_steps(W, W + K)
-    host_enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / (K * R)
     ms = eng.timer_stop()
     barrier()
     launches = (eng.kernel_launches() - launches0) // R

@@ -366,7 +366,8 @@ static int create_impl(sbr_model* m) {
   const bool sampled = c.loss >= SBR_LOSS_BPR && c.loss <= SBR_LOSS_BLACKOUT;
   const bool margin = c.loss >= SBR_LOSS_HINGE;
   const size_t n_cells = (size_t)m->global_batch + std::max(1, c.n_samples);
-  if ((rc = dev_alloc(m, &m->logits, B * std::max<size_t>(m->N, n_cells)))) return rc;
+  // rows padded to a multiple of 4 floats: 16-byte row pitch, so the score matrix can be a TMA operand of the gradient GEMMs
+  if ((rc = dev_alloc(m, &m->logits, B * (size_t)round_up(std::max<size_t>(m->N, n_cells), 4)))) return rc;
   if ((rc = dev_alloc(m, &m->row_loss, B))) return rc;
   if (sampled) {
     if ((rc = dev_alloc(m, &m->cells, n_cells))) return rc;
@@ -819,7 +820,7 @@ static int output_backward_full(sbr_model* m, int B) {
   const int N = m->N, H = m->H_last;
   int rc;
   // critical path: dh_last feeds the BPTT scan
-  if ((rc = launch_gemm(m, false, false, B, H, N, m->logits, N, m->params + m->out_WT, H, m->dh_last, H, 1.f, 0.f))) return rc;
+  if ((rc = launch_gemm(m, false, false, B, H, N, m->logits, (int)round_up(N, 4), m->params + m->out_WT, H, m->dh_last, H, 1.f, 0.f))) return rc;
   // off the critical path: dW_out^T and db_out go to the side stream (joined before the all-reduce).  The fork point
   // is here (they only need the logit gradients and h_last), but the launches are issued AFTER the BPTT scan has
   // been launched on the main stream (launch_deferred_output_grads): a GEMM that reaches the SMs first would keep
@@ -839,8 +840,8 @@ static int launch_deferred_output_grads(sbr_model* m) {
     CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
     std::swap(m->stream, m->side);
   }
-  int rc = launch_gemm(m, true, false, N, H, B, m->logits, N, m->h_last, H, m->grads + m->out_WT, H, 1.f, 1.f);
-  if (!rc) rc = launch_colsum(m, m->logits, B, N, N, m->grads + m->out_b);
+  int rc = launch_gemm(m, true, false, N, H, B, m->logits, (int)round_up(N, 4), m->h_last, H, m->grads + m->out_WT, H, 1.f, 1.f);
+  if (!rc) rc = launch_colsum(m, m->logits, B, N, (int)round_up(N, 4), m->grads + m->out_b);
   if (side) {
     std::swap(m->stream, m->side);
     m->side_pending = true;
@@ -904,8 +905,8 @@ static int step_cce(sbr_model* m, const BatchSlot& s, float* cost) {
   const float inv_gb = 1.f / (float)(m->cfg.global_batch > 0 ? m->cfg.global_batch : s.B * m->cfg.n_ranks);
   if ((rc = forward_stack(m, s))) return rc;
   const int B = s.B, N = m->N, H = m->H_last;
-  if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, N, 1.f, 0.f))) return rc;
-  if ((rc = launch_cce(m, m->logits, N, m->params + m->out_b, s.Y, s.pop, B, N, inv_gb, m->row_loss))) return rc;
+  if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, (int)round_up(N, 4), 1.f, 0.f))) return rc;
+  if ((rc = launch_cce(m, m->logits, (int)round_up(N, 4), m->params + m->out_b, s.Y, s.pop, B, N, inv_gb, m->row_loss))) return rc;
   if ((rc = launch_reduce_cost(m, m->row_loss, B, m->grads + m->cost_slot))) return rc;
   if (m->cfg.regularization != 0.f)
     if ((rc = launch_bias_reg(m, m->params + m->out_b, m->grads + m->out_b, N, m->cfg.regularization / (float)m->cfg.n_ranks,
@@ -984,17 +985,18 @@ extern "C" int sbr_train_step_sampled(sbr_model* m, const int32_t* X, const floa
   const float inv_gb = 1.f / (float)(m->cfg.global_batch > 0 ? m->cfg.global_batch : s.B * m->cfg.n_ranks);
   if ((rc = forward_stack(m, s))) return rc;
   const int H = m->H_last;
+  const int ldc = (int)round_up(nc, 4);      // padded row pitch of the [B, n_all + S] score matrix
   float* bcg = m->bc + nc;   // gradient of the gathered bias entries
   // BlackoutLayer: scores of the gathered columns only (sparse_lstm.py:41-54)
   if ((rc = launch_gather_table_rows(m, m->params + m->out_WT, m->params + m->out_b, m->cells, nc, H, m->Wc, m->bc))) return rc;
-  if ((rc = launch_gemm(m, false, true, B, nc, H, m->h_last, H, m->Wc, H, m->logits, nc, 1.f, 0.f))) return rc;
-  if ((rc = launch_sampling_loss(m, loss, m->cfg.last_layer_tanh != 0, m->logits, nc, m->bc, s.pop, B, n_all, row_offset, S, inv_gb, m->row_loss))) return rc;
+  if ((rc = launch_gemm(m, false, true, B, nc, H, m->h_last, H, m->Wc, H, m->logits, ldc, 1.f, 0.f))) return rc;
+  if ((rc = launch_sampling_loss(m, loss, m->cfg.last_layer_tanh != 0, m->logits, ldc, m->bc, s.pop, B, n_all, row_offset, S, inv_gb, m->row_loss))) return rc;
   if ((rc = launch_reduce_cost(m, m->row_loss, B, m->grads + m->cost_slot))) return rc;
-  if ((rc = launch_gemm(m, true, false, nc, H, B, m->logits, nc, m->h_last, H, m->dWc, H, 1.f, 0.f))) return rc;
+  if ((rc = launch_gemm(m, true, false, nc, H, B, m->logits, ldc, m->h_last, H, m->dWc, H, 1.f, 0.f))) return rc;
   CU_TRY(m, cudaMemsetAsync(bcg, 0, (size_t)nc * sizeof(float), m->stream));
-  if ((rc = launch_colsum(m, m->logits, B, nc, nc, bcg))) return rc;
+  if ((rc = launch_colsum(m, m->logits, B, nc, ldc, bcg))) return rc;
   if ((rc = launch_scatter_table_rows(m, m->dWc, bcg, m->cells, nc, H, m->grads + m->out_WT, m->grads + m->out_b))) return rc;
-  if ((rc = launch_gemm(m, false, false, B, H, nc, m->logits, nc, m->Wc, H, m->dh_last, H, 1.f, 0.f))) return rc;
+  if ((rc = launch_gemm(m, false, false, B, H, nc, m->logits, ldc, m->Wc, H, m->dh_last, H, 1.f, 0.f))) return rc;
   stage_mark(m, 4);
   if ((rc = backward_stack(m, s))) return rc;
   return finish_step(m, cost);
@@ -1007,12 +1009,13 @@ static int step_margin(sbr_model* m, const BatchSlot& s, float* cost, const Marg
   const float inv_gb = 1.f / (float)(m->cfg.global_batch > 0 ? m->cfg.global_batch : s.B * m->cfg.n_ranks);
   if ((rc = forward_stack(m, s))) return rc;
   const int B = s.B, N = m->N, H = m->H_last;
-  if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, N, 1.f, 0.f))) return rc;
+  const int ldl = (int)round_up(N, 4);
+  if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, ldl, 1.f, 0.f))) return rc;
   if (rg.on) {
-    if ((rc = launch_margin_loss_ragged(m, m->cfg.loss, m->logits, N, m->params + m->out_b, m->tgt_off, m->tgt_ids, s.X, s.len, m->w_neg,
+    if ((rc = launch_margin_loss_ragged(m, m->cfg.loss, m->logits, ldl, m->params + m->out_b, m->tgt_off, m->tgt_ids, s.X, s.len, m->w_neg,
                                         rg.has_default ? m->def_tgt : nullptr, rg.exclude_seen, B, m->T, m->K, N, rg.max_special, inv_gb,
                                         m->row_loss))) return rc;
-  } else if ((rc = launch_margin_loss(m, m->cfg.loss, m->logits, N, m->params + m->out_b, m->mY, m->mW, B, N, inv_gb, m->row_loss))) return rc;
+  } else if ((rc = launch_margin_loss(m, m->cfg.loss, m->logits, ldl, m->params + m->out_b, m->mY, m->mW, B, N, inv_gb, m->row_loss))) return rc;
   if ((rc = launch_reduce_cost(m, m->row_loss, B, m->grads + m->cost_slot))) return rc;
   if ((rc = output_backward_full(m, B))) return rc;
   stage_mark(m, 4);
@@ -1087,9 +1090,10 @@ static int scores_device(sbr_model* m, const int32_t* X, const float* mask, int 
   m->profiling = prof;
   if (rc) return rc;
   const int N = m->N, H = m->H_last;
-  if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, N, 1.f, 0.f))) return rc;
-  if (softmax) return launch_softmax_rows(m, m->logits, N, m->params + m->out_b, B, N);
-  return launch_add_bias_rows(m, m->logits, N, m->params + m->out_b, B, N);
+  const int ldl = (int)round_up(N, 4);
+  if ((rc = launch_gemm(m, false, true, B, N, H, m->h_last, H, m->params + m->out_WT, H, m->logits, ldl, 1.f, 0.f))) return rc;
+  if (softmax) return launch_softmax_rows(m, m->logits, ldl, m->params + m->out_b, B, N);
+  return launch_add_bias_rows(m, m->logits, ldl, m->params + m->out_b, B, N);
 }
 
 extern "C" int sbr_scores(sbr_model* m, const int32_t* X, const float* mask, int B, int softmax, float* scores) {
@@ -1098,7 +1102,8 @@ extern "C" int sbr_scores(sbr_model* m, const int32_t* X, const float* mask, int
   const int sm = (m->cfg.loss == SBR_LOSS_CCE) || softmax;
   int rc = scores_device(m, X, mask, B, sm);
   if (rc) return rc;
-  CU_TRY(m, cudaMemcpyAsync(scores, m->logits, (size_t)B * m->N * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpy2DAsync(scores, (size_t)m->N * sizeof(float), m->logits, (size_t)round_up(m->N, 4) * sizeof(float),
+                              (size_t)m->N * sizeof(float), B, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   return 0;
 }
@@ -1123,7 +1128,7 @@ extern "C" int sbr_topk(sbr_model* m, const int32_t* X, const float* mask, int B
     if (ne > 0) CU_TRY(m, cudaMemcpyAsync(m->excl_ids, excl_ids, (size_t)ne * sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
     d_off = m->excl_off;
   }
-  if ((rc = launch_topk(m, m->logits, m->N, B, m->N, d_off, m->excl_ids, k, (mode >> 1) & 1, m->topk_ids))) return rc;
+  if ((rc = launch_topk(m, m->logits, (int)round_up(m->N, 4), B, m->N, d_off, m->excl_ids, k, (mode >> 1) & 1, m->topk_ids))) return rc;
   CU_TRY(m, cudaMemcpyAsync(ids_out, m->topk_ids, (size_t)B * k * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   return 0;

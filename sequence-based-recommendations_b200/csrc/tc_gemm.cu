@@ -475,36 +475,57 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
     };
 
     if constexpr (EPI == EPI_STORE) {
+      // TMEM holds the tile with one ROW per thread; written straight from there a warp store would touch 32 different
+      // rows.  Each warp therefore transposes 32 rows x 32 columns through a shared-memory patch (the raw ring is idle by
+      // now) and writes full 128-byte row segments: lane = (row within a group of 4, 16-byte column chunk).
       const bool atomic_out = gridDim.z > 1;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float d[16];
-        load_d(c0, d);
-        if (row < a.M && n0 + c0 < a.N) {
+      constexpr int PITCH = 36;                                    // floats per patch row: 16-byte aligned, conflict-free
+      float* patch = reinterpret_cast<float*>(rawA0) + warp * 32 * PITCH;
+      const int r_in = lane >> 3, c4 = (lane & 7) * 4;             // read-back position: row r_in (+4 per pass), columns c4..c4+3
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        {
+          float d[16];
+          load_d(c0, d);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const int col = n0 + c0 + i;
-            if (col >= a.N) break;
-            float o[4];
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(patch + lane * PITCH + i) = make_float4(d[i], d[i + 1], d[i + 2], d[i + 3]);
+          if (c0 + 16 < BN) {
+            load_d(c0 + 16, d);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = a.alpha * d[i + e] + ((a.bias && col + e < a.N && blockIdx.z == 0) ? __ldg(a.bias + col + e) : 0.f);
-            float* dst = a.C + (long long)row * a.ldc + col;
-            const bool v4 = a.c_vec && col + 3 < a.N;
-            if (atomic_out) {
-              if (v4) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
-              else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) if (col + e < a.N) atomicAdd(dst + e, o[e]);
-              }
-            } else if (v4) {
-              float4 r = make_float4(o[0], o[1], o[2], o[3]);
-              if (a.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst); r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
-              *reinterpret_cast<float4*>(dst) = r;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) if (col + e < a.N) dst[e] = a.accumulate ? dst[e] + o[e] : o[e];
-            }
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(patch + lane * PITCH + 16 + i) = make_float4(d[i], d[i + 1], d[i + 2], d[i + 3]);
           }
         }
+        __syncwarp();
+        const int col = n0 + c0 + c4;
+        const bool col_in = col < a.N && c0 + c4 < BN;
+        float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.bias && blockIdx.z == 0 && col_in) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (col + e < a.N) bias4[e] = __ldg(a.bias + col + e);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int grow = m0 + warp * 32 + rr + r_in;
+          if (grow >= a.M || !col_in) continue;
+          const float4 v = *reinterpret_cast<const float4*>(patch + (rr + r_in) * PITCH + c4);
+          float o[4] = {a.alpha * v.x + bias4[0], a.alpha * v.y + bias4[1], a.alpha * v.z + bias4[2], a.alpha * v.w + bias4[3]};
+          float* dst = a.C + (long long)grow * a.ldc + col;
+          const bool v4 = a.c_vec && col + 3 < a.N;
+          if (atomic_out) {
+            if (v4) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+            else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (col + e < a.N) atomicAdd(dst + e, o[e]);
+            }
+          } else if (v4) {
+            float4 r = make_float4(o[0], o[1], o[2], o[3]);
+            if (a.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst); r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
+            *reinterpret_cast<float4*>(dst) = r;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (col + e < a.N) dst[e] = a.accumulate ? dst[e] + o[e] : o[e];
+          }
+        }
+        __syncwarp();
       }
     }
 

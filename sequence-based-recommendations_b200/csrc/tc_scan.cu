@@ -1074,9 +1074,12 @@ int launch_cluster_coop(sbr_model* m, Kern kern, dim3 grid, dim3 cl, size_t smem
   attr[0].val.clusterDim.x = cl.x; attr[0].val.clusterDim.y = cl.y; attr[0].val.clusterDim.z = cl.z;
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
-  cfg.attrs = attr; cfg.numAttrs = 2;
+  // SBR_SCAN_NO_COOP: plain cluster launch (Nsight Compute cannot replay a cooperative cluster launch; the grid is sized
+  // to be co-resident on an otherwise idle GPU)
+  static const bool no_coop = getenv("SBR_SCAN_NO_COOP") != nullptr;
+  cfg.attrs = attr; cfg.numAttrs = no_coop ? 1 : 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
-  if (e != cudaSuccess) {
+  if (e != cudaSuccess && !no_coop) {
     // cooperative + cluster not accepted together: the grid is sized to be co-resident, launch it as a plain cluster grid
     cudaGetLastError();
     cfg.numAttrs = 1;
