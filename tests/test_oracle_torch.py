@@ -92,3 +92,143 @@ def test_oracle_matches_torch_autograd(cell, gc):
         assert max(abs(a - b).max() for a, b in zip(gfree, g0)) > 1e-6
     for (n, _), a, b in zip(O.param_names_shapes(spec), g0, g1):
         np.testing.assert_allclose(a, b.reshape(a.shape), rtol=1e-9, atol=1e-13, err_msg=n)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Losses and updaters: a second derivation that does not share code with the oracle.  The torch graphs below are
+# written from the reference's own expressions (rnn_sampling.py:68-91,137; sparse_lstm.py:41-54; rnn_margin.py:61-68,
+# 109) on top of a hidden state h; torch.autograd supplies the gradients.  The updaters are torch.optim where torch
+# implements the same rule (Adagrad, RMSprop, Adadelta, SGD with Nesterov momentum match lasagne up to the documented
+# reparametrisations) and a hand-written restatement of lasagne.updates.adam (its bias correction is folded into the
+# step size, which torch.optim.Adam does differently: eps is applied after the correction there).
+# ------------------------------------------------------------------------------------------------------------
+def _torch_head_sampling(spec, h, W, b, Y, samples, pop):
+    B = h.shape[0]
+    cells = torch.cat([torch.tensor(Y).long(), torch.tensor(samples).long()])
+    pred = h @ W[:, cells] + b[cells]                      # BlackoutLayer, sparse_lstm.py:49-54
+    if spec.loss == "Blackout":
+        p = torch.softmax(pred, dim=1)
+        pos = -torch.log(p[torch.arange(B), torch.arange(B)])
+        neg = torch.log(1 - p)
+        loss = pos - neg[:, B:].sum(dim=-1)
+    else:
+        if spec.last_layer_tanh:
+            pred = torch.tanh(pred)
+        diff = (pred - torch.diag(pred)[:, None])[:, B:]
+        if spec.loss == "BPR":
+            loss = -torch.log(torch.sigmoid(-diff)).mean(dim=-1)
+        elif spec.loss == "BPRI":
+            loss = torch.log(torch.sigmoid(diff)).mean(dim=-1)
+        else:
+            loss = (torch.sigmoid(diff) + torch.sigmoid(pred[:, B:] ** 2)).mean(dim=-1)
+    return (loss / torch.tensor(pop)).mean()
+
+
+def _torch_head_margin(spec, h, W, b, Ymat, Wmat):
+    pred = h @ W + b
+    Yt, Wt = torch.tensor(Ymat), torch.tensor(Wmat)
+    if spec.loss == "hinge":
+        x = (pred - Yt) * Wt
+        loss = (0.5 * (x + x.abs())).sum(dim=-1)           # T.nnet.relu = 0.5 (x + |x|)
+    elif spec.loss == "logit":
+        loss = (torch.sigmoid(pred - Yt) * Wt).sum(dim=-1)
+    else:
+        loss = -torch.log(torch.sigmoid((Yt - pred) * Wt)).sum(dim=-1)
+    return loss.mean()
+
+
+@pytest.mark.parametrize("loss,tanh", [("BPR", False), ("BPR", True), ("BPRI", False), ("TOP1", True), ("Blackout", False)])
+def test_sampling_losses_match_torch_autograd(loss, tanh):
+    rng = np.random.RandomState(5)
+    N, H, B, S = 23, 7, 6, 4
+    spec = O.Spec(n_items=N, cell="GRU", layers=(H,), loss=loss, last_layer_tanh=tanh)
+    P = {"out.W": rng.normal(0, 0.4, (H, N)), "out.b": rng.normal(0, 0.2, N)}
+    h = rng.normal(0, 0.8, (B, H))
+    Y = rng.randint(0, N, B)
+    samples = rng.randint(0, N, S)
+    samples[0] = Y[2]                                     # a sample colliding with a target: no filtering in the reference
+    pop = rng.uniform(0.5, 2, B)
+    c0, dh0, dW0, db0 = O.sampling_loss(spec, P, h, Y, samples, pop)
+    ht = torch.tensor(h, requires_grad=True)
+    Wt = torch.tensor(P["out.W"], requires_grad=True)
+    bt = torch.tensor(P["out.b"], requires_grad=True)
+    c1 = _torch_head_sampling(spec, ht, Wt, bt, Y, samples, pop)
+    c1.backward()
+    assert abs(float(c0) - c1.item()) < 1e-12
+    np.testing.assert_allclose(dh0, ht.grad.numpy(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(dW0, Wt.grad.numpy(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(db0, bt.grad.numpy(), rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("loss", ["hinge", "logit", "logsig"])
+def test_margin_losses_match_torch_autograd(loss):
+    rng = np.random.RandomState(6)
+    N, H, B = 19, 5, 4
+    spec = O.Spec(n_items=N, cell="GRU", layers=(H,), loss=loss)
+    P = {"out.W": rng.normal(0, 0.5, (H, N)), "out.b": rng.normal(0, 0.2, N)}
+    h = rng.normal(0, 0.8, (B, H))
+    in_seqs = [list(rng.choice(N, size=3 + b, replace=False)) for b in range(B)]
+    targets = [list(rng.choice(N, size=1 + b % 2, replace=False)) for b in range(B)]
+    Ymat, Wmat = O.margin_targets(N, in_seqs, targets)
+    c0, dh0, dW0, db0 = O.margin_loss(spec, P, h, Ymat, Wmat)
+    ht = torch.tensor(h, requires_grad=True)
+    Wt = torch.tensor(P["out.W"], requires_grad=True)
+    bt = torch.tensor(P["out.b"], requires_grad=True)
+    c1 = _torch_head_margin(spec, ht, Wt, bt, Ymat, Wmat)
+    c1.backward()
+    assert abs(float(c0) - c1.item()) < 1e-12
+    np.testing.assert_allclose(dh0, ht.grad.numpy(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(dW0, Wt.grad.numpy(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(db0, bt.grad.numpy(), rtol=1e-9, atol=1e-13)
+
+
+def _lasagne_adam_by_hand(p, grads, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """lasagne.updates.adam restated independently of the oracle: one shared t, the bias
+    correction folded into the step size a_t, eps added to sqrt(v) WITHOUT correction."""
+    m = np.zeros_like(p); v = np.zeros_like(p)
+    for t, g in enumerate(grads, 1):
+        a_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        p = p - a_t * m / (np.sqrt(v) + eps)
+    return p
+
+
+@pytest.mark.parametrize("kind", ["adam", "adagrad", "rmsprop", "adadelta", "nesterov"])
+def test_updaters_match_an_independent_implementation(kind):
+    rng = np.random.RandomState(8)
+    p0 = rng.normal(0, 1, (4, 3))
+    grads = [rng.normal(0, 1, (4, 3)) for _ in range(6)]
+    lr, rho = 0.05, 0.9
+    upd = O.Updater(kind, lr=lr, rho=rho)
+    p = [p0.copy()]
+    for g in grads:
+        upd.step(p, [g])
+    if kind == "adam":
+        ref = _lasagne_adam_by_hand(p0.copy(), grads, lr=lr)
+    else:
+        pt = torch.tensor(p0.copy(), requires_grad=True)
+        if kind == "adagrad":       # lasagne: p -= lr g / sqrt(acc + eps); torch: lr g / (sqrt(acc) + eps) -> eps -> 0 on both sides
+            opt = torch.optim.Adagrad([pt], lr=lr, eps=0.0)
+        elif kind == "rmsprop":
+            opt = torch.optim.RMSprop([pt], lr=lr, alpha=rho, eps=0.0)
+        elif kind == "adadelta":
+            opt = torch.optim.Adadelta([pt], lr=lr, rho=rho, eps=1e-6)
+        else:                       # lasagne nesterov_momentum: v = mu v - lr g; p += mu v - lr g  == SGD(nesterov) on the scaled velocity
+            opt = torch.optim.SGD([pt], lr=lr, momentum=rho, nesterov=True)
+        for g in grads:
+            opt.zero_grad()
+            pt.grad = torch.tensor(g)
+            opt.step()
+        ref = pt.detach().numpy()
+    # adagrad / rmsprop place eps INSIDE the square root in lasagne (sqrt(acc + 1e-6)) and outside in torch (here 0):
+    # elements whose accumulator is ~1e-6 differ at the 1e-4 level, everything else agrees to rounding
+    tol = 1e-3 if kind in ("adagrad", "rmsprop") else 1e-12
+    np.testing.assert_allclose(p[0], ref, rtol=tol, atol=tol)
+    if kind in ("adagrad", "rmsprop"):
+        # exact check against the documented lasagne rule, restated here without the oracle
+        q, acc = p0.copy(), np.zeros_like(p0)
+        for g in grads:
+            acc = acc + g * g if kind == "adagrad" else rho * acc + (1 - rho) * g * g
+            q = q - lr * g / np.sqrt(acc + 1e-6)
+        np.testing.assert_allclose(p[0], q, rtol=1e-12, atol=1e-12)
