@@ -41,7 +41,7 @@ extern "C" {
 #define SBR_API
 #endif
 
-#define SBR_ABI_VERSION 1
+#define SBR_ABI_VERSION 2
 #define SBR_MAX_LAYERS 8
 #define SBR_NCCL_ID_BYTES 128
 
@@ -90,6 +90,7 @@ typedef struct sbr_config {
   int32_t rank;
   int32_t global_batch;             /* rows over all ranks; 0 -> batch_size * n_ranks          */
   int32_t n_slots;                  /* device-resident batch slots (>=1), see sbr_stage_*      */
+  int32_t bidirectional;            /* --r_bi: every depth = forward + backwards layer, concatenated (recurrent_layers.py:72-78) */
   uint8_t nccl_id[SBR_NCCL_ID_BYTES]; /* from sbr_nccl_unique_id on rank 0, shared by the host */
 } sbr_config;
 

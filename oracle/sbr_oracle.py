@@ -46,6 +46,7 @@ class Spec:
     regularization: float = 0.0       # rnn_one_hot.py:73-77 (output bias only)
     last_layer_tanh: bool = False     # rnn_sampling.py:19
     last_layer_init: float = 1.0      # rnn_sampling.py:19,131
+    bidirectional: bool = False       # recurrent_layers.py:11,72-78 (--r_bi): every level = concat(forward, backward layer)
 
     @property
     def n_in(self) -> int:
@@ -59,6 +60,11 @@ class Spec:
 # --------------------------------------------------------------------------------------
 # Parameter list (checkpoint order)
 # --------------------------------------------------------------------------------------
+
+def layer_prefixes(spec: Spec, li: int) -> List[str]:
+    """Parameter-name prefixes of the directional layers of depth li: ['l0.'] or ['l0.', 'l0b.']."""
+    return ["l%d." % li, "l%db." % li] if spec.bidirectional else ["l%d." % li]
+
 
 def param_names_shapes(spec: Spec) -> List[Tuple[str, Tuple[int, ...]]]:
     """Names and shapes in lasagne.layers.get_all_params order.
@@ -76,27 +82,46 @@ def param_names_shapes(spec: Spec) -> List[Tuple[str, Tuple[int, ...]]]:
     else:
         n_inputs = spec.n_in
     for li, H in enumerate(spec.layers):
-        pre = "l%d." % li
         if spec.cell == "LSTM":
             gate_names = ["ingate", "forgetgate", "cell", "outgate"]
         elif spec.cell == "GRU":
             gate_names = ["updategate", "resetgate", "hidden_update"]
         else:
             gate_names = ["hidden_update"]
-        for g in gate_names:
-            out.append((pre + "W_in_to_" + g, (n_inputs, H)))
-            out.append((pre + "W_hid_to_" + g, (H, H)))
-            out.append((pre + "b_" + g, (H,)))
-        if spec.cell == "LSTM":
-            out.append((pre + "W_cell_to_ingate", (H,)))
-            out.append((pre + "W_cell_to_forgetgate", (H,)))
-            out.append((pre + "W_cell_to_outgate", (H,)))
-            out.append((pre + "cell_init", (1, H)))
-        out.append((pre + "hid_init", (1, H)))
-        n_inputs = H
-    out.append(("out.W", (spec.layers[-1], spec.n_items)))
+        # bidirectional: the forward layer's parameters, then the backward layer's, per depth (recurrent_layers.py:73-76)
+        for pre in layer_prefixes(spec, li):
+            if dense_vanilla(spec, li):
+                # lasagne.layers.RecurrentLayer (recurrent_layers.py:98-99): CustomRecurrentLayer.get_params lists its
+                # own hid_init first, then input_to_hidden (W, b), then hidden_to_hidden (W; no bias)
+                out.append((pre + "hid_init", (1, H)))
+                out.append((pre + "W_in_to_hid", (n_inputs, H)))
+                out.append((pre + "b", (H,)))
+                out.append((pre + "W_hid_to_hid", (H, H)))
+                continue
+            for g in gate_names:
+                out.append((pre + "W_in_to_" + g, (n_inputs, H)))
+                out.append((pre + "W_hid_to_" + g, (H, H)))
+                out.append((pre + "b_" + g, (H,)))
+            if spec.cell == "LSTM":
+                out.append((pre + "W_cell_to_ingate", (H,)))
+                out.append((pre + "W_cell_to_forgetgate", (H,)))
+                out.append((pre + "W_cell_to_outgate", (H,)))
+                out.append((pre + "cell_init", (1, H)))
+            out.append((pre + "hid_init", (1, H)))
+        n_inputs = H * (2 if spec.bidirectional else 1)
+    out.append(("out.W", (spec.layers[-1] * (2 if spec.bidirectional else 1), spec.n_items)))
     out.append(("out.b", (spec.n_items,)))
     return out
+
+
+def dense_vanilla(spec: Spec, li: int) -> bool:
+    """A Vanilla layer whose input is dense -- deeper layers of a stack, or any layer behind an embedding -- is Lasagne's
+    own RecurrentLayer, not the in-tree VanillaLayerOHEInput (recurrent_layers.py:86-87 vs :98-99).  Lasagne is a
+    third-party dependency that is not in the reference tree (the reference's README pins Lasagne 0.2.dev1); its
+    published RecurrentLayer: h_t = rectify(x_t W_in + b + h_{t-1} W_hid), one grad_clip on the summed pre-activation,
+    W_in_to_hid / W_hid_to_hid ~ Uniform(-0.01, 0.01), b = 0, learned hid_init = 0.  The in-tree sparse copy uses tanh
+    (sparse_lstm.py:960-961), so a Vanilla stack mixes tanh (layer 0 without embedding) and rectifiers (the rest)."""
+    return spec.cell == "Vanilla" and (li > 0 or spec.embedding > 0)
 
 
 def init_params(spec: Spec, rng: np.random.RandomState, dtype=np.float64) -> List[np.ndarray]:
@@ -116,6 +141,8 @@ def init_params(spec: Spec, rng: np.random.RandomState, dtype=np.float64) -> Lis
             std = gain * np.sqrt(2.0 / (shape[0] + shape[1]))
             a = np.sqrt(3.0) * std
             v = rng.uniform(-a, a, size=shape)
+        elif leaf in ("W_in_to_hid", "W_hid_to_hid"):
+            v = rng.uniform(-0.01, 0.01, size=shape)      # lasagne.init.Uniform() of RecurrentLayer
         elif leaf.startswith("W_"):
             v = rng.normal(0.0, 0.1, size=shape)
         else:
@@ -124,14 +151,16 @@ def init_params(spec: Spec, rng: np.random.RandomState, dtype=np.float64) -> Lis
     return vals
 
 
-def _stack(spec: Spec, P: Dict[str, np.ndarray], li: int):
+def _stack(spec: Spec, P: Dict[str, np.ndarray], li):
     """Stack per-gate matrices the way get_output_for does.
 
     LSTM stacks [in, forget, cell, out] (sparse_lstm.py:348-360); GRU stacks
     [reset, update, hidden] (sparse_lstm.py:737-749) although the params were *created*
     update-first; Vanilla has a single block (sparse_lstm.py:1098-1104).
     """
-    pre = "l%d." % li
+    pre = li if isinstance(li, str) else "l%d." % li
+    if pre + "W_in_to_hid" in P:                      # Lasagne RecurrentLayer (dense_vanilla)
+        return P[pre + "W_in_to_hid"], P[pre + "W_hid_to_hid"], P[pre + "b"], None
     if spec.cell == "LSTM":
         order = ["ingate", "forgetgate", "cell", "outgate"]
     elif spec.cell == "GRU":
@@ -159,7 +188,7 @@ def _sigmoid(x):
 # Recurrent stack forward / backward
 # --------------------------------------------------------------------------------------
 
-def _layer_forward(spec: Spec, li: int, P, Xg, mask):
+def _layer_forward(spec: Spec, li: int, P, Xg, mask, pre=None, backwards=False):
     """One recurrent layer over time-major Xg [T,B,G*H], mask [T,B].
 
     LSTM step: sparse_lstm.py:377-415; GRU step: :764-796; Vanilla step: :1120-1143; masked
@@ -167,18 +196,21 @@ def _layer_forward(spec: Spec, li: int, P, Xg, mask):
     :817-819.
     Returns hs [T,B,H] (state after each step) and a cache for the backward pass.
     """
-    _, W_hid, _, _ = _stack(spec, P, li)
+    pre = pre or "l%d." % li
+    _, W_hid, _, _ = _stack(spec, P, pre)
     T, B, _ = Xg.shape
     H = spec.layers[li]
-    pre = "l%d." % li
     dt = Xg.dtype
     h = np.repeat(P[pre + "hid_init"], B, axis=0).astype(dt)
     c = np.repeat(P[pre + "cell_init"], B, axis=0).astype(dt) if spec.cell == "LSTM" else None
     if spec.cell == "LSTM":
         w_ci, w_cf, w_co = (P[pre + "W_cell_to_ingate"], P[pre + "W_cell_to_forgetgate"], P[pre + "W_cell_to_outgate"])
     hs = np.zeros((T, B, H), dtype=dt)
-    cache = []
-    for t in range(T):
+    cache = [None] * T
+    # a backwards layer scans the padded arrays from the last position to the first (theano.scan go_backwards, as
+    # Lasagne does for backwards=True): the padding comes first and carries the initial state, then the row's items
+    # in reverse; hs[t] stays aligned with the input position t (Lasagne reverses the scan output back)
+    for t in (range(T - 1, -1, -1) if backwards else range(T)):
         m = mask[t][:, None] > 0
         if spec.cell == "LSTM":
             gates = Xg[t] + h @ W_hid
@@ -188,7 +220,7 @@ def _layer_forward(spec: Spec, li: int, P, Xg, mask):
             c_new = f * c + i * g
             o = _sigmoid(gates[:, 3 * H:4 * H] + c_new * w_co)
             h_new = o * np.tanh(c_new)
-            cache.append((h, c, i, f, g, o, c_new, m))
+            cache[t] = (h, c, i, f, g, o, c_new, m)
             c = np.where(m, c_new, c)
             h = np.where(m, h_new, h)
         elif spec.cell == "GRU":
@@ -198,17 +230,18 @@ def _layer_forward(spec: Spec, li: int, P, Xg, mask):
             u = _sigmoid(a[:, H:2 * H] + x[:, H:2 * H])
             cand = np.tanh(x[:, 2 * H:3 * H] + r * a[:, 2 * H:3 * H])
             h_new = (1 - u) * h + u * cand
-            cache.append((h, a, r, u, cand, m))
+            cache[t] = (h, a, r, u, cand, m)
             h = np.where(m, h_new, h)
         else:
-            h_new = np.tanh(Xg[t] + h @ W_hid)
-            cache.append((h, h_new, m))
+            z = Xg[t] + h @ W_hid
+            h_new = np.maximum(z, 0) if dense_vanilla(spec, li) else np.tanh(z)
+            cache[t] = (h, h_new, m)
             h = np.where(m, h_new, h)
         hs[t] = h
     return hs, cache
 
 
-def _layer_backward(spec: Spec, li: int, P, cache, dhs, G_out):
+def _layer_backward(spec: Spec, li: int, P, cache, dhs, G_out, pre=None, backwards=False):
     """BPTT through one layer (derived from the forward above).
 
     dhs [T,B,H]: external gradient arriving at the layer output of every step (zero except the
@@ -217,14 +250,14 @@ def _layer_backward(spec: Spec, li: int, P, cache, dhs, G_out):
     grad_clip sites: LSTM sparse_lstm.py:386-388; GRU :768-772 and :789-791; Vanilla
     :1125-1129 and :1138-1140.
     """
-    _, W_hid, _, order = _stack(spec, P, li)
+    pre = pre or "l%d." % li
+    _, W_hid, _, order = _stack(spec, P, pre)
     T = len(cache)
     H = spec.layers[li]
     G = spec.G
     B = dhs.shape[1]
     gc = spec.grad_clip
     dt = dhs.dtype
-    pre = "l%d." % li
     dXg = np.zeros((T, B, G * H), dtype=dt)
     dW_hid = np.zeros_like(W_hid)
     dh = np.zeros((B, H), dtype=dt)
@@ -236,7 +269,7 @@ def _layer_backward(spec: Spec, li: int, P, cache, dhs, G_out):
     if spec.cell == "LSTM":
         w_ci, w_cf, w_co = (P[pre + "W_cell_to_ingate"], P[pre + "W_cell_to_forgetgate"], P[pre + "W_cell_to_outgate"])
         dw_ci = np.zeros(H, dtype=dt); dw_cf = np.zeros(H, dtype=dt); dw_co = np.zeros(H, dtype=dt)
-    for t in range(T - 1, -1, -1):
+    for t in (range(T) if backwards else range(T - 1, -1, -1)):      # reverse of the processing order
         dh = dh + dhs[t]
         if spec.cell == "LSTM":
             h_prev, c_prev, i, f, g, o, c_new, m = cache[t]
@@ -271,14 +304,16 @@ def _layer_backward(spec: Spec, li: int, P, cache, dhs, G_out):
         else:
             h_prev, h_new, m = cache[t]
             mz = m.astype(dt)
-            dq = clip(dh * (1 - h_new * h_new)) * mz
+            dq = clip(dh * ((h_new > 0).astype(dt) if dense_vanilla(spec, li) else 1 - h_new * h_new)) * mz
             dx = clip(dq)
             da = clip(dq)
             dXg[t] = dx
             dW_hid += h_prev.T @ da
             dh = np.where(m, da @ W_hid.T, dh)
     # split stacked dW_hid back into per-gate gradients
-    for gi, gname in enumerate(order):
+    if order is None:
+        G_out[pre + "W_hid_to_hid"] = dW_hid
+    for gi, gname in enumerate(order or ()):
         G_out[pre + "W_hid_to_" + gname] = dW_hid[:, gi * H:(gi + 1) * H]
     if spec.cell == "LSTM":
         G_out[pre + "W_cell_to_ingate"] = dw_ci
@@ -294,7 +329,10 @@ def forward_stack(spec: Spec, P, X, mask):
 
     OHE gather-sum for layer 0 without embedding (sparse_lstm.py:368,755,1111); embedding +
     dense precompute otherwise (recurrent_layers.py:47-50, Lasagne precompute_input);
-    time-major dimshuffle (sparse_lstm.py:343-344).
+    time-major dimshuffle (sparse_lstm.py:343-344).  Bidirectional (recurrent_layers.py:72-78): every depth is a
+    forward and a backwards layer over the same input, concatenated along the features; the final state is
+    [forward state after the last position | backward state after the first position] (only_return_final takes the
+    last SCAN step of each direction).
     """
     X = np.asarray(X)
     if X.ndim == 2:
@@ -305,54 +343,74 @@ def forward_stack(spec: Spec, P, X, mask):
     Xt = np.transpose(X, (1, 0, 2))                  # [T,B,K]
     caches = []
     inp = None
+    finals = []
     for li in range(len(spec.layers)):
-        W_in, _, b, _ = _stack(spec, P, li)
-        if li == 0 and spec.embedding == 0:
-            Xg = W_in[Xt, :].sum(axis=-2) + b
-        elif li == 0:
-            inp = P["emb.W"][Xt, :].reshape(T, B, K * spec.embedding)
-            Xg = inp @ W_in + b
-        else:
-            Xg = inp @ W_in + b
-        hs, cache = _layer_forward(spec, li, P, Xg, maskT)
-        caches.append((inp, cache))
-        inp = hs
-    h_last = inp[-1]
+        outs, level = [], []
+        finals = []
+        for di, pre in enumerate(layer_prefixes(spec, li)):
+            W_in, _, b, _ = _stack(spec, P, pre)
+            if li == 0 and spec.embedding == 0:
+                Xg = W_in[Xt, :].sum(axis=-2) + b
+            elif li == 0:
+                inp = P["emb.W"][Xt, :].reshape(T, B, K * spec.embedding)
+                Xg = inp @ W_in + b
+            else:
+                Xg = inp @ W_in + b
+            hs, cache = _layer_forward(spec, li, P, Xg, maskT, pre=pre, backwards=(di == 1))
+            outs.append(hs)
+            finals.append(hs[0] if di == 1 else hs[-1])
+            level.append(cache)
+        caches.append((inp, level))
+        inp = np.concatenate(outs, axis=-1) if len(outs) > 1 else outs[0]
+    h_last = np.concatenate(finals, axis=-1) if len(finals) > 1 else finals[0]
     return h_last, (Xt, maskT, caches)
 
 
 def backward_stack(spec: Spec, P, fwd_cache, dh_last, G_out):
-    """Back-propagate dh_last [B,H] through the stack; fills G_out with every stack gradient."""
+    """Back-propagate dh_last [B,H_out] through the stack; fills G_out with every stack gradient."""
     Xt, maskT, caches = fwd_cache
     T, B, K = Xt.shape
     dt = dh_last.dtype
     L = len(spec.layers)
-    dhs = np.zeros((T, B, spec.layers[-1]), dtype=dt)
-    dhs[-1] = dh_last
+    nd = 2 if spec.bidirectional else 1
+    Htop = spec.layers[-1]
+    dhs_dir = []
+    for di in range(nd):
+        d = np.zeros((T, B, Htop), dtype=dt)
+        d[0 if di == 1 else -1] = dh_last[:, di * Htop:(di + 1) * Htop]
+        dhs_dir.append(d)
     for li in range(L - 1, -1, -1):
-        inp, cache = caches[li]
-        W_in, _, _, order = _stack(spec, P, li)
+        inp, level = caches[li]
         H = spec.layers[li]
-        pre = "l%d." % li
-        dXg = _layer_backward(spec, li, P, cache, dhs, G_out)
-        db = dXg.sum(axis=(0, 1))
-        if li == 0 and spec.embedding == 0:
-            dW_in = np.zeros_like(W_in)
-            # AdvancedIncSubtensor1: duplicates accumulate (grad of sparse_lstm.py:368)
-            np.add.at(dW_in, Xt.reshape(-1), np.repeat(dXg.reshape(T * B, -1), K, axis=0))
-            dinp = None
-        else:
-            flat_in = inp.reshape(T * B, -1)
-            dW_in = flat_in.T @ dXg.reshape(T * B, -1)
-            dinp = (dXg.reshape(T * B, -1) @ W_in.T).reshape(inp.shape)
-        for gi, gname in enumerate(order):
-            G_out[pre + "W_in_to_" + gname] = dW_in[:, gi * H:(gi + 1) * H]
-            G_out[pre + "b_" + gname] = db[gi * H:(gi + 1) * H]
+        dinp_total = None
+        for di, pre in enumerate(layer_prefixes(spec, li)):
+            W_in, _, _, order = _stack(spec, P, pre)
+            dXg = _layer_backward(spec, li, P, level[di], dhs_dir[di], G_out, pre=pre, backwards=(di == 1))
+            db = dXg.sum(axis=(0, 1))
+            if li == 0 and spec.embedding == 0:
+                dW_in = np.zeros_like(W_in)
+                # AdvancedIncSubtensor1: duplicates accumulate (grad of sparse_lstm.py:368)
+                np.add.at(dW_in, Xt.reshape(-1), np.repeat(dXg.reshape(T * B, -1), K, axis=0))
+                dinp = None
+            else:
+                flat_in = inp.reshape(T * B, -1)
+                dW_in = flat_in.T @ dXg.reshape(T * B, -1)
+                dinp = (dXg.reshape(T * B, -1) @ W_in.T).reshape(inp.shape)
+            if order is None:
+                G_out[pre + "W_in_to_hid"] = dW_in
+                G_out[pre + "b"] = db
+            for gi, gname in enumerate(order or ()):
+                G_out[pre + "W_in_to_" + gname] = dW_in[:, gi * H:(gi + 1) * H]
+                G_out[pre + "b_" + gname] = db[gi * H:(gi + 1) * H]
+            if dinp is not None:
+                dinp_total = dinp if dinp_total is None else dinp_total + dinp
         if li == 0 and spec.embedding > 0:
             dE = np.zeros_like(P["emb.W"])
-            np.add.at(dE, Xt.reshape(-1), dinp.reshape(T * B * K, spec.embedding))
+            np.add.at(dE, Xt.reshape(-1), dinp_total.reshape(T * B * K, spec.embedding))
             G_out["emb.W"] = dE
-        dhs = dinp
+        if li > 0:
+            Hb = spec.layers[li - 1]
+            dhs_dir = [dinp_total[:, :, di * Hb:(di + 1) * Hb] for di in range(nd)]
 
 
 # --------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ class SbrConfig(C.Structure):
         ("lr", C.c_float), ("rho", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
         ("grad_clip", C.c_float), ("regularization", C.c_float),
         ("math_mode", C.c_int32), ("device", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32),
-        ("global_batch", C.c_int32), ("n_slots", C.c_int32),
+        ("global_batch", C.c_int32), ("n_slots", C.c_int32), ("bidirectional", C.c_int32),
         ("nccl_id", C.c_uint8 * SBR_NCCL_ID_BYTES),
     ]
 
@@ -107,8 +107,8 @@ def load_library():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.sbr_abi_version() != 1:
-        raise ImportError("libsbr_b200.so ABI %d, binding expects 1" % lib.sbr_abi_version())
+    if lib.sbr_abi_version() != 2:
+        raise ImportError("libsbr_b200.so ABI %d, binding expects 2" % lib.sbr_abi_version())
     _lib = lib
     return lib
 
@@ -141,7 +141,7 @@ class Engine(object):
                  embedding=0, n_extra_ids=0, ids_per_step=1, n_samples=32, last_layer_tanh=False,
                  updater="adam", lr=1e-3, rho=0.9, beta1=0.9, beta2=0.999, grad_clip=100.0,
                  regularization=0.0, device=0, n_ranks=1, rank=0, nccl_id=None, global_batch=0,
-                 n_slots=1, math_mode=0):
+                 n_slots=1, math_mode=0, bidirectional=False):
         self.lib = load_library()
         cfg = SbrConfig()
         cfg.struct_size = C.sizeof(SbrConfig)
@@ -160,6 +160,7 @@ class Engine(object):
         cfg.grad_clip, cfg.regularization = grad_clip, regularization
         cfg.math_mode, cfg.device, cfg.n_ranks, cfg.rank = int(math_mode), int(device), int(n_ranks), int(rank)
         cfg.global_batch, cfg.n_slots = int(global_batch), int(n_slots)
+        cfg.bidirectional = int(bool(bidirectional))
         if n_ranks > 1:
             if nccl_id is None or len(nccl_id) != SBR_NCCL_ID_BYTES:
                 raise ValueError("n_ranks > 1 needs the 128-byte nccl_id made by nccl_unique_id() on rank 0")

@@ -42,6 +42,9 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- model description ----------------------------------------------------------------------
 struct LayerDesc {
+  int level = 0;       // depth in the stack
+  int relu = 0;        // Vanilla cell fed by a dense input (Lasagne RecurrentLayer): rectifier instead of tanh
+  int dir = 0;         // 0 forward layer, 1 backwards layer of a bidirectional stack (runs on row-reversed inputs)
   int H = 0;           // hidden units
   int G = 0;           // stacked gate blocks: LSTM 4 [in,forget,cell,out], GRU 3 [reset,update,hidden], Vanilla 1
   int I = 0;           // dense input width; 0 = id gather-sum layer (layer 0 without embedding)
@@ -108,6 +111,7 @@ struct sbr_model {
 
   // geometry
   int B = 0, T = 0, K = 1, N = 0, n_in = 0, E = 0, L = 0, H_last = 0;
+  int nd = 1;              // directional layers per depth (2 with --r_bi); layers[level * nd + dir]
   int global_batch = 0;
   std::vector<LayerDesc> layers;
   std::vector<ParamView> views;
@@ -127,6 +131,13 @@ struct sbr_model {
   std::vector<BatchSlot> slots;
   float* emb_out = nullptr;   // [T*B, K*E]
   float* demb = nullptr;
+  // bidirectional stacks: the backwards layers run the forward-only scan kernels on rows whose valid prefix is reversed
+  int32_t* X_rev = nullptr;   // [B, T, K] ids with every row's valid prefix reversed
+  float* emb_out_rv = nullptr; float* demb_rv = nullptr;       // embedding path in reversed coordinates
+  float* cat_al = nullptr;    // [T*B, 2*maxH] level output [forward | backward] aligned with the input positions
+  float* cat_rv = nullptr;    // [T*B, 2*maxH] the same in reversed coordinates (input of the backwards layers)
+  float* dcat_al = nullptr; float* dcat_rv = nullptr;          // their gradients
+  float* h_last_dir = nullptr; float* dh_last_dir = nullptr;   // [2][B, H_top] per-direction final states / gradients
   float* h_last = nullptr;    // [B, H_last]
   float* dh_last = nullptr;   // [B, H_last]
   float* logits = nullptr;    // [B, max(N, n_all+S)]
@@ -203,6 +214,12 @@ int launch_gather_table_rows(sbr_model* m, const float* table, const float* bias
                              int ncols, float* out_rows, float* out_bias);
 int launch_scatter_table_rows(sbr_model* m, const float* rows, const float* brow, const int32_t* ids, int n_ids,
                               int ncols, float* table_grad, float* bias_grad);
+// bidirectional plumbing (gather_scatter.cu)
+int launch_reverse_ids(sbr_model* m, const int32_t* X, const int32_t* len, int32_t* X_rev, int B, int T, int K);
+int launch_bi_concat(sbr_model* m, const float* hs_f, const float* hs_b, const int32_t* len, float* cat_al, float* cat_rv,
+                     int B, int t_max, int H);
+int launch_bi_split(sbr_model* m, const float* dcat_al, const float* dcat_rv, const int32_t* len, float* dhs_f, float* dhs_b,
+                    int B, int t_max, int H);
 int launch_transpose(sbr_model* m, const float* in, int rows, int cols, int ld_in, float* out);
 int launch_embed_gather(sbr_model* m, const int32_t* X, const int32_t* len, const float* table, float* out,
                         int B, int T, int K, int E, int t_max);

@@ -314,3 +314,82 @@ int launch_embed_scatter(sbr_model* m, const int32_t* X, const int32_t* len, con
   KERNEL_CHECK(m);
   return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Bidirectional stacks (recurrent_layers.py:72-78).  A backwards layer over left-aligned rows equals a forward layer
+// over the rows with their valid prefix reversed, and its output un-reversed the same way is the aligned output
+// (DESIGN.md section 3.5 states the identity; the CPU tests check it), so the backwards layers reuse
+// the forward-only scan kernels; these kernels move data between the two coordinate systems.  Time-major rows
+// (row = t*B + b); position t of row b maps to len_b - 1 - t.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void reverse_ids_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ len, int32_t* __restrict__ Xr,
+                                   int B, int T, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T * K) return;
+  const int k = (int)(i % K), t = (int)((i / K) % T), b = (int)(i / ((int64_t)K * T));
+  const int l = min(len[b], T);
+  Xr[i] = t < l ? X[((int64_t)b * T + (l - 1 - t)) * K + k] : 0;
+}
+// cat_al[(t,b)] = [hs_f(t,b) | hs_b(l-1-t,b)],  cat_rv[(t,b)] = [hs_f(l-1-t,b) | hs_b(t,b)];  zero beyond the row's length
+__global__ void bi_concat_kernel(const float* __restrict__ hs_f, const float* __restrict__ hs_b, const int32_t* __restrict__ len,
+                                 float* __restrict__ cat_al, float* __restrict__ cat_rv, int B, int t_max, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)t_max * B * H) return;
+  const int k = (int)(i % H);
+  const int64_t row = i / H;
+  const int b = (int)(row % B), t = (int)(row / B);
+  const int l = min(len[b], t_max);
+  float f_al = 0.f, b_al = 0.f, f_rv = 0.f, b_rv = 0.f;
+  if (t < l) {
+    const int64_t mir = (int64_t)(l - 1 - t) * B + b;
+    f_al = hs_f[row * H + k]; b_rv = hs_b[row * H + k];
+    f_rv = hs_f[mir * H + k]; b_al = hs_b[mir * H + k];
+  }
+  cat_al[row * 2 * H + k] = f_al; cat_al[row * 2 * H + H + k] = b_al;
+  cat_rv[row * 2 * H + k] = f_rv; cat_rv[row * 2 * H + H + k] = b_rv;
+}
+// dhs_f(t,b) = dcat_al(t,b)[0:H] + dcat_rv(l-1-t,b)[0:H];  dhs_b(t,b) = dcat_al(l-1-t,b)[H:2H] + dcat_rv(t,b)[H:2H]
+__global__ void bi_split_kernel(const float* __restrict__ dcat_al, const float* __restrict__ dcat_rv, const int32_t* __restrict__ len,
+                                float* __restrict__ dhs_f, float* __restrict__ dhs_b, int B, int t_max, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)t_max * B * H) return;
+  const int k = (int)(i % H);
+  const int64_t row = i / H;
+  const int b = (int)(row % B), t = (int)(row / B);
+  const int l = min(len[b], t_max);
+  float df = 0.f, db = 0.f;
+  if (t < l) {
+    const int64_t mir = (int64_t)(l - 1 - t) * B + b;
+    df = dcat_al[row * 2 * H + k] + dcat_rv[mir * 2 * H + k];
+    db = dcat_al[mir * 2 * H + H + k] + dcat_rv[row * 2 * H + H + k];
+  }
+  dhs_f[row * H + k] = df;
+  dhs_b[row * H + k] = db;
+}
+}  // namespace
+
+int launch_reverse_ids(sbr_model* m, const int32_t* X, const int32_t* len, int32_t* X_rev, int B, int T, int K) {
+  const int64_t n = (int64_t)B * T * K;
+  if (n == 0) return 0;
+  reverse_ids_kernel<<<cdiv(n, 256), 256, 0, m->stream>>>(X, len, X_rev, B, T, K);
+  KERNEL_CHECK(m);
+  return 0;
+}
+int launch_bi_concat(sbr_model* m, const float* hs_f, const float* hs_b, const int32_t* len, float* cat_al, float* cat_rv,
+                     int B, int t_max, int H) {
+  const int64_t n = (int64_t)t_max * B * H;
+  if (n == 0) return 0;
+  bi_concat_kernel<<<cdiv(n, 256), 256, 0, m->stream>>>(hs_f, hs_b, len, cat_al, cat_rv, B, t_max, H);
+  KERNEL_CHECK(m);
+  return 0;
+}
+int launch_bi_split(sbr_model* m, const float* dcat_al, const float* dcat_rv, const int32_t* len, float* dhs_f, float* dhs_b,
+                    int B, int t_max, int H) {
+  const int64_t n = (int64_t)t_max * B * H;
+  if (n == 0) return 0;
+  bi_split_kernel<<<cdiv(n, 256), 256, 0, m->stream>>>(dcat_al, dcat_rv, len, dhs_f, dhs_b, B, t_max, H);
+  KERNEL_CHECK(m);
+  return 0;
+}

@@ -182,13 +182,33 @@ static int build_layout(sbr_model* m) {
   }
   int n_inputs = m->E > 0 ? m->E * m->K : m->n_in;
   for (int li = 0; li < m->L; ++li) {
+   for (int dir = 0; dir < m->nd; ++dir) {       // bidirectional: the forward layer's parameters, then the backwards layer's
     LayerDesc L;
+    L.level = li; L.dir = dir;
     L.H = c.layers[li];
     L.G = c.cell == SBR_CELL_LSTM ? 4 : (c.cell == SBR_CELL_GRU ? 3 : 1);
     L.I = (li == 0 && m->E == 0) ? 0 : n_inputs;
     L.in_rows = n_inputs;
     const int H = L.H, GH = L.G * L.H;
+    const std::string pre = "l" + std::to_string(li) + (dir ? "b." : ".");
+    // A Vanilla layer with a dense input is Lasagne's own RecurrentLayer (recurrent_layers.py:98-99), not the in-tree
+    // sparse copy: rectifier instead of tanh, parameters listed hid_init, W_in_to_hid, b, W_hid_to_hid.
+    L.relu = (c.cell == SBR_CELL_VANILLA && L.I > 0) ? 1 : 0;
+    if (L.relu) {
+      L.h_init = take(off, H);
+      add_view(m, pre + "hid_init", 2, 1, H, L.h_init, 1, H, H);
+    }
     L.W_in = take(off, (int64_t)n_inputs * GH);
+    if (L.relu) {
+      L.b = take(off, GH);
+      L.W_hid = take(off, (int64_t)H * GH);
+      add_view(m, pre + "W_in_to_hid", 2, n_inputs, H, L.W_in, n_inputs, H, GH);
+      add_view(m, pre + "b", 1, H, 1, L.b, 1, H, H);
+      add_view(m, pre + "W_hid_to_hid", 2, H, H, L.W_hid, H, H, GH);
+      m->P += (int64_t)n_inputs * GH + (int64_t)H * GH + GH + H;
+      m->layers.push_back(L);
+      continue;
+    }
     L.W_hid = take(off, (int64_t)H * GH);
     L.b = take(off, GH);
     m->P += (int64_t)n_inputs * GH + (int64_t)H * GH + GH;
@@ -199,7 +219,6 @@ static int build_layout(sbr_model* m) {
     }
     L.h_init = take(off, H);
     m->P += H;
-    const std::string pre = "l" + std::to_string(li) + ".";
     // creation order of the gates in the reference vs. position in the stacked matrices
     struct GateRef { const char* name; int sidx; };
     std::vector<GateRef> gates;
@@ -219,9 +238,10 @@ static int build_layout(sbr_model* m) {
     }
     add_view(m, pre + "hid_init", 2, 1, H, L.h_init, 1, H, H);
     m->layers.push_back(L);
-    n_inputs = H;
+   }
+    n_inputs = c.layers[li] * m->nd;
   }
-  m->H_last = m->layers.back().H;
+  m->H_last = m->layers.back().H * m->nd;
   m->out_WT = take(off, (int64_t)m->N * m->H_last);
   m->out_b = take(off, m->N);
   m->P += (int64_t)m->N * m->H_last + m->N;
@@ -243,7 +263,7 @@ extern "C" void sbr_destroy(sbr_model* m) {
   F(m->params); F(m->grads); F(m->opt_a); F(m->opt_b);
   for (LayerDesc& L : m->layers) { F(L.Xg); F(L.act); F(L.hs); F(L.cs); F(L.dXg); F(L.dac); F(L.dhs); F(L.hT); F(L.aT); }
   for (BatchSlot& s : m->slots) { F(s.X); F(s.len); F(s.Y); F(s.pop); }
-  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe); F(m->scan_sync); F(m->ds_off); F(m->ds_ids); F(m->ds_rows);
+  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe); F(m->scan_sync); F(m->ds_off); F(m->ds_ids); F(m->ds_rows); F(m->X_rev); F(m->emb_out_rv); F(m->demb_rv); F(m->cat_al); F(m->cat_rv); F(m->dcat_al); F(m->dcat_rv); F(m->h_last_dir); F(m->dh_last_dir);
   F(m->mY); F(m->mW); F(m->cells); F(m->Wc); F(m->dWc); F(m->bc);
   F(m->tgt_off); F(m->tgt_ids); F(m->w_neg); F(m->def_tgt); F(m->excl_off); F(m->excl_ids); F(m->topk_ids);
   if (m->h_len) cudaFreeHost(m->h_len);
@@ -335,7 +355,7 @@ static int create_impl(sbr_model* m) {
     if (L.G == 4 && (rc = dev_alloc(m, &L.cs, (TB + B) * H))) return rc;
     if ((rc = dev_alloc(m, &L.dXg, TB * GH))) return rc;
     if (L.G == 3 && (rc = dev_alloc(m, &L.dac, TB * H))) return rc;
-    if (li + 1 < m->layers.size() && (rc = dev_alloc(m, &L.dhs, TB * H))) return rc;
+    if (L.level + 1 < m->L && (rc = dev_alloc(m, &L.dhs, TB * H))) return rc;
     // K-major pre-split copies for the tensor-core weight-gradient GEMM (only where the tcgen05 scans run)
     if (tc_scan_applies(L.G, L.H) && m->B % 16 == 0 && !m->disable_tc && !getenv("SBR_DISABLE_TC_WGRAD")) {
       const size_t rq_h = (TB + B) / 4, rq_a = TB / 4;
@@ -363,6 +383,23 @@ static int create_impl(sbr_model* m) {
   }
   if ((rc = dev_alloc(m, &m->h_last, B * m->H_last))) return rc;
   if ((rc = dev_alloc(m, &m->dh_last, B * m->H_last))) return rc;
+  if (m->nd == 2) {
+    size_t maxH = 0;
+    for (const LayerDesc& L : m->layers) maxH = std::max<size_t>(maxH, L.H);
+    if ((rc = dev_alloc(m, &m->X_rev, TB * m->K))) return rc;
+    if ((rc = dev_alloc(m, &m->h_last_dir, 2 * B * maxH))) return rc;
+    if ((rc = dev_alloc(m, &m->dh_last_dir, 2 * B * maxH))) return rc;
+    if (m->L > 1) {
+      if ((rc = dev_alloc(m, &m->cat_al, TB * 2 * maxH))) return rc;
+      if ((rc = dev_alloc(m, &m->cat_rv, TB * 2 * maxH))) return rc;
+      if ((rc = dev_alloc(m, &m->dcat_al, TB * 2 * maxH))) return rc;
+      if ((rc = dev_alloc(m, &m->dcat_rv, TB * 2 * maxH))) return rc;
+    }
+    if (m->E > 0) {
+      if ((rc = dev_alloc(m, &m->emb_out_rv, TB * m->K * m->E))) return rc;
+      if ((rc = dev_alloc(m, &m->demb_rv, TB * m->K * m->E))) return rc;
+    }
+  }
   const bool sampled = c.loss >= SBR_LOSS_BPR && c.loss <= SBR_LOSS_BLACKOUT;
   const bool margin = c.loss >= SBR_LOSS_HINGE;
   const size_t n_cells = (size_t)m->global_batch + std::max(1, c.n_samples);
@@ -434,7 +471,7 @@ extern "C" int sbr_create(const sbr_config* cfg, sbr_model** out) {
   auto bad = [&](const char* what) { sbr_set_error(nullptr, SBR_E_ARG, "unsupported configuration: %s", what); return SBR_E_ARG; };
   if (cfg->cell < 0 || cfg->cell > SBR_CELL_VANILLA) return bad("cell");
   if (cfg->n_layers < 1 || cfg->n_layers > SBR_MAX_LAYERS) return bad("n_layers");
-  if (cfg->cell == SBR_CELL_VANILLA && cfg->n_layers > 1) return bad("stacked Vanilla layers (Lasagne RecurrentLayer) are not on the supported path");
+  if (cfg->bidirectional != 0 && cfg->bidirectional != 1) return bad("bidirectional must be 0 or 1");
   for (int i = 0; i < cfg->n_layers; ++i)
     if (cfg->layers[i] < 1 || cfg->layers[i] > 512) return bad("layer size must be in [1, 512]");
   if (cfg->n_items < 1 || cfg->n_extra_ids < 0 || cfg->ids_per_step < 1 || cfg->embedding < 0) return bad("sizes");
@@ -454,6 +491,7 @@ extern "C" int sbr_create(const sbr_config* cfg, sbr_model** out) {
   m->dev = cfg->device;
   m->B = cfg->batch_size; m->T = cfg->max_length; m->K = cfg->ids_per_step; m->N = cfg->n_items;
   m->n_in = cfg->n_items + cfg->n_extra_ids; m->E = cfg->embedding; m->L = cfg->n_layers;
+  m->nd = cfg->bidirectional ? 2 : 1;
   m->global_batch = cfg->global_batch > 0 ? cfg->global_batch : cfg->batch_size * cfg->n_ranks;
   const int rc = create_impl(m);
   if (rc != 0) {
@@ -705,34 +743,57 @@ static int bias_rows(sbr_model* m, float* out, const float* bias, int64_t rows, 
   return 0;
 }
 
-// ids -> final hidden state of the top layer (m->h_last)
+// ids -> final hidden state of the top level (m->h_last; [forward | backward] for a bidirectional stack)
 static int forward_stack(sbr_model* m, const BatchSlot& s) {
   m->cur_hlen = (int)s.hlen.size() == s.B ? s.hlen.data() : nullptr;
-  const int B = s.B, T = m->T, K = m->K, t_max = s.t_max;
+  const int B = s.B, T = m->T, K = m->K, t_max = s.t_max, nd = m->nd;
   const int64_t rows = (int64_t)t_max * B;
   int rc;
   stage_mark(m, 1);
+  if (nd == 2 && (rc = launch_reverse_ids(m, s.X, s.len, m->X_rev, B, T, K))) return rc;
   for (int li = 0; li < m->L; ++li) {
-    LayerDesc& L = m->layers[li];
-    const int GH = L.G * L.H;
-    if (li == 0 && m->E == 0) {
-      if ((rc = launch_gather_rows(m, s.X, s.len, m->params + L.W_in, m->params + L.b, L.Xg, B, T, K, GH, t_max, m->n_in))) return rc;
-      stage_mark(m, 2);
-    } else {
-      const float* in;
-      int I;
-      if (li == 0) {
-        if ((rc = launch_embed_gather(m, s.X, s.len, m->params + m->emb_W, m->emb_out, B, T, K, m->E, t_max))) return rc;
-        in = m->emb_out; I = K * m->E;
+    for (int dir = 0; dir < nd; ++dir) {
+      LayerDesc& L = m->layers[li * nd + dir];
+      const int GH = L.G * L.H;
+      const int32_t* X = dir ? m->X_rev : s.X;       // the backwards layer sees every row reversed
+      if (li == 0 && m->E == 0) {
+        if ((rc = launch_gather_rows(m, X, s.len, m->params + L.W_in, m->params + L.b, L.Xg, B, T, K, GH, t_max, m->n_in))) return rc;
       } else {
-        in = m->layers[li - 1].hs + (int64_t)B * m->layers[li - 1].H;   // skip the init row block
-        I = m->layers[li - 1].H;
+        const float* in;
+        int I;
+        if (li == 0) {
+          float* eo = dir ? m->emb_out_rv : m->emb_out;
+          if ((rc = launch_embed_gather(m, X, s.len, m->params + m->emb_W, eo, B, T, K, m->E, t_max))) return rc;
+          in = eo; I = K * m->E;
+        } else if (nd == 1) {
+          in = m->layers[li - 1].hs + (int64_t)B * m->layers[li - 1].H;   // skip the init row block
+          I = m->layers[li - 1].H;
+        } else {
+          in = dir ? m->cat_rv : m->cat_al;
+          I = 2 * m->layers[(li - 1) * nd].H;
+        }
+        if ((rc = launch_gemm_bias(m, false, (int)rows, GH, I, in, I, m->params + L.W_in, GH, L.Xg, GH, m->params + L.b))) return rc;
       }
-      if ((rc = launch_gemm_bias(m, false, (int)rows, GH, I, in, I, m->params + L.W_in, GH, L.Xg, GH, m->params + L.b))) return rc;
-      if (li == 0) stage_mark(m, 2);
+      if (li == 0 && dir == nd - 1) stage_mark(m, 2);
+      float* h_last = nullptr;
+      if (li == m->L - 1) h_last = nd == 1 ? m->h_last : m->h_last_dir + (size_t)dir * B * L.H;
+      if ((rc = launch_rnn_forward(m, L, s.len, B, t_max, h_last))) return rc;
     }
-    float* h_last = (li == m->L - 1) ? m->h_last : nullptr;
-    if ((rc = launch_rnn_forward(m, L, s.len, B, t_max, h_last))) return rc;
+    if (nd == 2) {
+      const LayerDesc& Lf = m->layers[li * 2];
+      const LayerDesc& Lb = m->layers[li * 2 + 1];
+      const int H = Lf.H;
+      if (li < m->L - 1) {
+        // outputs of this depth for the next one, in both coordinate systems
+        if ((rc = launch_bi_concat(m, Lf.hs + (int64_t)B * H, Lb.hs + (int64_t)B * H, s.len, m->cat_al, m->cat_rv, B, t_max, H))) return rc;
+      } else {
+        // final state = [forward state after the last item | backward state after the first item]
+        CU_TRY(m, cudaMemcpy2DAsync(m->h_last, (size_t)2 * H * sizeof(float), m->h_last_dir, (size_t)H * sizeof(float),
+                                    (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, m->stream));
+        CU_TRY(m, cudaMemcpy2DAsync(m->h_last + H, (size_t)2 * H * sizeof(float), m->h_last_dir + (size_t)B * H, (size_t)H * sizeof(float),
+                                    (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, m->stream));
+      }
+    }
   }
   stage_mark(m, 3);
   return 0;
@@ -740,55 +801,85 @@ static int forward_stack(sbr_model* m, const BatchSlot& s) {
 
 static int side_fork(sbr_model* m);
 static int side_return(sbr_model* m);
+static int side_join(sbr_model* m);
 static int launch_deferred_output_grads(sbr_model* m);
 
 // BPTT through the stack given m->dh_last; fills the gradient arena of every stack parameter
 static int backward_stack(sbr_model* m, const BatchSlot& s) {
   m->cur_hlen = (int)s.hlen.size() == s.B ? s.hlen.data() : nullptr;
-  const int B = s.B, T = m->T, K = m->K, t_max = s.t_max;
+  const int B = s.B, T = m->T, K = m->K, t_max = s.t_max, nd = m->nd;
   const int rows = t_max * B;
   int rc;
+  if (nd == 2) {
+    const int H = m->layers.back().H;     // split [forward | backward] of the gradient wrt the final state
+    CU_TRY(m, cudaMemcpy2DAsync(m->dh_last_dir, (size_t)H * sizeof(float), m->dh_last, (size_t)2 * H * sizeof(float),
+                                (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, m->stream));
+    CU_TRY(m, cudaMemcpy2DAsync(m->dh_last_dir + (size_t)B * H, (size_t)H * sizeof(float), m->dh_last + H, (size_t)2 * H * sizeof(float),
+                                (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, m->stream));
+  }
   for (int li = m->L - 1; li >= 0; --li) {
-    LayerDesc& L = m->layers[li];
-    const int H = L.H, GH = L.G * L.H;
-    if ((rc = launch_rnn_backward(m, L, s.len, B, t_max, li == m->L - 1 ? m->dh_last : nullptr))) return rc;
-    // the scan is in the launch queue first, so its clusters get their SMs before the side-stream GEMM's CTAs do
-    if (li == m->L - 1 && (rc = launch_deferred_output_grads(m))) return rc;
-    if (li == 0) stage_mark(m, 5);
-    const bool gather_layer = (li == 0 && m->E == 0);
-    if (gather_layer) {
-      // dW_in scatter on the side stream, concurrent with the weight-gradient GEMM below
-      if ((rc = side_fork(m))) return rc;
-      rc = launch_scatter_add_rows(m, s.X, s.len, L.dXg, m->grads + L.W_in, B, T, K, GH, t_max);
-      side_return(m);
-      m->side_pending = true;
-      if (rc) return rc;
+    for (int dir = 0; dir < nd; ++dir) {
+      LayerDesc& L = m->layers[li * nd + dir];
+      const int H = L.H, GH = L.G * L.H;
+      const float* dh_last = nullptr;
+      if (li == m->L - 1) dh_last = nd == 1 ? m->dh_last : m->dh_last_dir + (size_t)dir * B * H;
+      if ((rc = launch_rnn_backward(m, L, s.len, B, t_max, dh_last))) return rc;
+      // the scan is in the launch queue first, so its clusters get their SMs before the side-stream GEMM's CTAs do
+      if (li == m->L - 1 && dir == 0 && (rc = launch_deferred_output_grads(m))) return rc;
+      if (li == 0 && dir == nd - 1) stage_mark(m, 5);
+      const bool gather_layer = (li == 0 && m->E == 0);
+      const int32_t* X = dir ? m->X_rev : s.X;
+      if (gather_layer) {
+        // dW_in scatter on the side stream, concurrent with the weight-gradient GEMM below
+        if ((rc = side_fork(m))) return rc;
+        rc = launch_scatter_add_rows(m, X, s.len, L.dXg, m->grads + L.W_in, B, T, K, GH, t_max);
+        side_return(m);
+        m->side_pending = true;
+        if (rc) return rc;
+      }
+      // dW_hid = sum_t h_{t-1}^T da_t  : one tall-K GEMM outside the scan -- on tcgen05 from the K-major copies the
+      // tc scans wrote, else the generic GEMM (tcgen05 3xTF32 as well)
+      const bool tc_wgrad = L.hT && L.aT && B % 16 == 0 && rows % 8 == 0 && rows > 0 && !m->disable_tc_bwd;
+      if (tc_wgrad) {
+        if ((rc = launch_wgrad_tc(m, L, rows, m->grads + L.W_hid, GH))) return rc;
+      } else if (L.G == 3) {
+        if ((rc = launch_gemm(m, true, false, H, 2 * H, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
+        if ((rc = launch_gemm(m, true, false, H, H, rows, L.hs, H, L.dac, H, m->grads + L.W_hid + 2 * H, GH, 1.f, 1.f))) return rc;
+      } else {
+        if ((rc = launch_gemm(m, true, false, H, GH, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
+      }
+      // db = sum dXg: the tcgen05 BPTT kernels accumulate it themselves; the fallbacks need the column sum
+      if (!m->bwd_did_bias)
+        if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
+      if (li == 0 && dir == nd - 1) stage_mark(m, 6);
+      if (!gather_layer) {
+        const float* in;
+        float* din;
+        int I;
+        if (li == 0) {
+          in = dir ? m->emb_out_rv : m->emb_out; din = dir ? m->demb_rv : m->demb; I = K * m->E;
+        } else if (nd == 1) {
+          in = m->layers[li - 1].hs + (int64_t)B * m->layers[li - 1].H; din = m->layers[li - 1].dhs; I = m->layers[li - 1].H;
+        } else {
+          in = dir ? m->cat_rv : m->cat_al; din = dir ? m->dcat_rv : m->dcat_al; I = 2 * m->layers[(li - 1) * nd].H;
+        }
+        if ((rc = launch_gemm(m, true, false, I, GH, rows, in, I, L.dXg, GH, m->grads + L.W_in, GH, 1.f, 1.f))) return rc;
+        if ((rc = launch_gemm(m, false, true, rows, I, GH, L.dXg, GH, m->params + L.W_in, GH, din, I, 1.f, 0.f))) return rc;
+        if (li == 0)
+          if ((rc = launch_embed_scatter(m, X, s.len, din, m->grads + m->emb_W, B, T, K, m->E, t_max))) return rc;
+      }
     }
-    // dW_hid = sum_t h_{t-1}^T da_t  : one tall-K GEMM outside the scan -- on tcgen05 from the K-major copies the
-    // tc scans wrote, else the generic fp32 GEMM
-    const bool tc_wgrad = L.hT && L.aT && B % 16 == 0 && rows % 8 == 0 && rows > 0 && !m->disable_tc_bwd;
-    if (tc_wgrad) {
-      if ((rc = launch_wgrad_tc(m, L, rows, m->grads + L.W_hid, GH))) return rc;
-    } else if (L.G == 3) {
-      if ((rc = launch_gemm(m, true, false, H, 2 * H, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
-      if ((rc = launch_gemm(m, true, false, H, H, rows, L.hs, H, L.dac, H, m->grads + L.W_hid + 2 * H, GH, 1.f, 1.f))) return rc;
-    } else {
-      if ((rc = launch_gemm(m, true, false, H, GH, rows, L.hs, H, L.dXg, GH, m->grads + L.W_hid, GH, 1.f, 1.f))) return rc;
-    }
-    // db = sum dXg: the tcgen05 BPTT kernel accumulates it itself; the FFMA fallback needs the column sum
-    if (!m->bwd_did_bias)
-      if ((rc = launch_colsum(m, L.dXg, rows, GH, GH, m->grads + L.b))) return rc;
-    if (li == 0) stage_mark(m, 6);
-    if (!gather_layer) {
-      const float* in;
-      float* din;
-      int I;
-      if (li == 0) { in = m->emb_out; din = m->demb; I = K * m->E; }
-      else { in = m->layers[li - 1].hs + (int64_t)B * m->layers[li - 1].H; din = m->layers[li - 1].dhs; I = m->layers[li - 1].H; }
-      if ((rc = launch_gemm(m, true, false, I, GH, rows, in, I, L.dXg, GH, m->grads + L.W_in, GH, 1.f, 1.f))) return rc;
-      if ((rc = launch_gemm(m, false, true, rows, I, GH, L.dXg, GH, m->params + L.W_in, GH, din, I, 1.f, 0.f))) return rc;
-      if (li == 0)
-        if ((rc = launch_embed_scatter(m, s.X, s.len, m->demb, m->grads + m->emb_W, B, T, K, m->E, t_max))) return rc;
+    if (nd == 2 && li > 0) {
+      // gradients wrt the outputs of the depth below: un-concatenate, bring both contributions into each layer's own
+      // coordinate system, add.  The depth below needs ITS concatenated outputs again for its input-weight gradients.
+      LayerDesc& Pf = m->layers[(li - 1) * 2];
+      LayerDesc& Pb = m->layers[(li - 1) * 2 + 1];
+      if ((rc = launch_bi_split(m, m->dcat_al, m->dcat_rv, s.len, Pf.dhs, Pb.dhs, B, t_max, Pf.H))) return rc;
+      if (li - 1 > 0) {
+        const LayerDesc& Qf = m->layers[(li - 2) * 2];
+        const LayerDesc& Qb = m->layers[(li - 2) * 2 + 1];
+        if ((rc = launch_bi_concat(m, Qf.hs + (int64_t)B * Qf.H, Qb.hs + (int64_t)B * Qb.H, s.len, m->cat_al, m->cat_rv, B, t_max, Qf.H))) return rc;
+      }
     }
   }
   return 0;

@@ -59,6 +59,7 @@ struct RnnArgs {
   float* g_h_init;
   float* g_c_init;
   float clip;
+  int relu;            // vanilla cell: rectifier instead of tanh (dense-input layers)
   int B, H, Hs, t_max;
 };
 
@@ -238,7 +239,8 @@ __global__ void __launch_bounds__(NT, 1) rnn_fwd_kernel(const RnnArgs a) {
             float* ap = a.act + row * 4 * H + j0 + j;
             ap[0] = r; ap[H] = u; ap[2 * H] = cand; ap[3 * H] = ac;
           } else {
-            h_new = tanhf(xc[q][0] + pre[0]);
+            const float z = xc[q][0] + pre[0];
+            h_new = a.relu ? fmaxf(z, 0.f) : tanhf(z);
           }
         }
         // publish h_t[b, j0+j] to every CTA of the cluster (distributed shared memory)
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(NT, 1) rnn_bwd_kernel(const RnnArgs a) {
             carry_new = dh * (1.f - u);
           } else {
             const float h_new = sv[q][0];
-            const float dq = clipf_(dh * (1.f - h_new * h_new), a.clip);
+            const float dq = clipf_(dh * (a.relu ? (h_new > 0.f ? 1.f : 0.f) : 1.f - h_new * h_new), a.clip);
             da[0] = dq;
             dx[0] = dq;
             carry_new = 0.f;
@@ -633,7 +635,7 @@ int launch_rnn_forward(sbr_model* m, const LayerDesc& L, const int32_t* len, int
   a.Xg = L.Xg; a.W_hid = m->params + L.W_hid; a.W_hidT = nullptr;
   a.peep = m->params + L.peep; a.h_init = m->params + L.h_init; a.c_init = m->params + L.c_init;
   a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act; a.h_last = h_last;
-  a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.t_max = t_max;
+  a.clip = m->cfg.grad_clip; a.relu = L.relu; a.B = B; a.H = L.H; a.Hs = p.Hs; a.t_max = t_max;
   const int n_tiles = cdiv(B, p.BT);
   if (L.G == 4) return dispatch<4, false>(m, p, n_tiles, a);
   if (L.G == 3) return dispatch<3, false>(m, p, n_tiles, a);
@@ -667,7 +669,7 @@ int launch_rnn_backward(sbr_model* m, const LayerDesc& L, const int32_t* len, in
   a.peep = m->params + L.peep; a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act;
   a.dh_last = dh_last; a.dhs = dh_last ? nullptr : L.dhs; a.dXg = L.dXg; a.dac = L.dac;
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
-  a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.t_max = t_max;
+  a.clip = m->cfg.grad_clip; a.relu = L.relu; a.B = B; a.H = L.H; a.Hs = p.Hs; a.t_max = t_max;
   const int n_tiles = cdiv(B, p.BT);
   if (L.G == 4) return dispatch<4, true>(m, p, n_tiles, a);
   if (L.G == 3) return dispatch<3, true>(m, p, n_tiles, a);

@@ -49,6 +49,7 @@ struct TcArgs {
   float* hs; float* cs; float* act; float* h_last;
   const float* dh_last; const float* dhs; float* dXg; float* dac; float* g_peep; float* g_h_init; float* g_c_init;
   float clip;
+  int relu;            // vanilla cell: rectifier instead of tanh (dense-input layers)
   int B, H, Hs, Kp, t_max;
   long long* dbg;   // optional phase timeline of CTA 0 / thread 0 (8 stamps per step)
   float* hT; float* aT;                 // K-major pre-split copies for the tensor-core wgrad GEMM (may be null)
@@ -480,7 +481,8 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const __grid_cons
             hn[u] = (1.f - uu) * hp[u] + uu * cand;
             sv[u][0] = r; sv[u][1] = uu; sv[u][2] = cand; sv[u][3] = ac;
           } else {
-            hn[u] = tanhf_(xg[0] + pre[0]);
+            const float z = xg[0] + pre[0];
+            hn[u] = a.relu ? fmaxf(z, 0.f) : tanhf_(z);
           }
         }
       }
@@ -841,7 +843,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
           kc[u][2] = ac * r * (1.f - r);                  // dr_pre = dq * kc2
           kc[u][3] = 1.f - uu;                            // carry  = d * kc3
         } else {
-          kc[u][0] = 1.f - sv[0][u] * sv[0][u];           // dq = clip(d * kc0)
+          kc[u][0] = a.relu ? (sv[0][u] > 0.f ? 1.f : 0.f) : 1.f - sv[0][u] * sv[0][u];   // dq = clip(d * kc0)
         }
       }
     }
@@ -1268,7 +1270,7 @@ int launch_rnn_forward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len, 
   a.Xg = L.Xg; a.W_hid = m->params + L.W_hid; a.W_hidT = m->WhidT;
   a.peep = m->params + L.peep; a.h_init = m->params + L.h_init; a.c_init = m->params + L.c_init;
   a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act; a.h_last = h_last;
-  a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
+  a.clip = m->cfg.grad_clip; a.relu = L.relu; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   if (const char* e = getenv("SBR_TC_EXPERIMENT")) a.xflags = atoi(e);
   const TileSched sc = schedule_tiles(m, p, B, t_max, 0.71f);   // fwd: 2914 vs 4114 cycles per step (8 vs 16 rows)
   const int BT = sc.BT;
@@ -1328,7 +1330,7 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
   a.W_hid = m->params + L.W_hid; a.peep = m->params + L.peep; a.len = len; a.hs = L.hs; a.cs = L.cs; a.act = L.act;
   a.dh_last = dh_last; a.dhs = dh_last ? nullptr : L.dhs; a.dXg = L.dXg; a.dac = L.dac;
   a.g_peep = m->grads + L.peep; a.g_h_init = m->grads + L.h_init; a.g_c_init = m->grads + L.c_init;
-  a.clip = m->cfg.grad_clip; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
+  a.clip = m->cfg.grad_clip; a.relu = L.relu; a.B = B; a.H = L.H; a.Hs = p.Hs; a.Kp = p.Kp; a.t_max = t_max;
   const TileSched sc = schedule_tiles(m, p, B, t_max, 0.75f);   // bwd: 4118 vs 5477 cycles per step (8 vs 16 rows)
   const int BT = sc.BT;
   a.g_b = m->grads + L.b;

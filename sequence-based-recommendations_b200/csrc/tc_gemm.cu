@@ -62,6 +62,7 @@ struct StepArgs {
   float* carry; float* dcs; float* dpe;     // [B,H] scratch (dpe: [3][B,H])
   float* g_h_init; float* g_c_init; float* g_peep;
   float clip;
+  int relu;            // vanilla cell: rectifier instead of tanh (dense-input layers)
 };
 
 struct TgArgs {
@@ -570,7 +571,8 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
             hn[j] = (1.f - uu) * hp[j] + uu * cand;
             sv[0][j] = r; sv[1][j] = uu; sv[2][j] = cand; sv[3][j] = ac;
           } else {
-            hn[j] = tanh_fast(xg[0][j] + pre[j]);
+            const float z = xg[0][j] + pre[j];
+            hn[j] = s.relu ? fmaxf(z, 0.f) : tanh_fast(z);
           }
         }
         st8(s.hs_n + (long long)b * H + u0, hn);
@@ -635,7 +637,7 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
               carry_new = d * (1.f - uu);
             } else {
               const float h_new = __ldg(s.hs_r + idx);          // hs_r = state AFTER step t for the vanilla cell
-              dx[0] = clip_sym(d * (1.f - h_new * h_new), s.clip);
+              dx[0] = clip_sym(d * (s.relu ? (h_new > 0.f ? 1.f : 0.f) : 1.f - h_new * h_new), s.clip);
               carry_new = 0.f;
             }
           }
@@ -813,7 +815,7 @@ int launch_rnn_forward_steps(sbr_model* m, const LayerDesc& L, const int32_t* le
     a.tma_a = get_tmap(&a.tmA, L.hs, H, (uint64_t)(m->T + 1) * m->B, H, TG_KC, 128, true);
     a.tma_b = get_tmap(&a.tmB, m->params + L.W_hid, GH, H, GH, STEP_U, TG_KC, false);
   }
-  a.st.B = B; a.st.H = H; a.st.G = G; a.st.len = len; a.st.peep = m->params + L.peep;
+  a.st.B = B; a.st.H = H; a.st.G = G; a.st.len = len; a.st.peep = m->params + L.peep; a.st.relu = L.relu;
   const dim3 grid(cdiv(H, STEP_U), cdiv(B, 128), 1);
   for (int t = 0; t < t_max; ++t) {
     a.a_off = t * B;       // rows t*B .. of the state trajectory
@@ -860,7 +862,7 @@ int launch_rnn_backward_steps(sbr_model* m, const LayerDesc& L, const int32_t* l
     if (G == 3) a.tma_b = a.tma_b && get_tmap(&a.tmB2, L.dac, H, (uint64_t)m->T * m->B, H, TG_KC, STEP_BN, true);
   }
   StepArgs& s = a.st;
-  s.B = B; s.H = H; s.G = G; s.len = len; s.peep = m->params + L.peep; s.clip = m->cfg.grad_clip;
+  s.B = B; s.H = H; s.G = G; s.len = len; s.peep = m->params + L.peep; s.clip = m->cfg.grad_clip; s.relu = L.relu;
   s.carry = m->step_carry; s.dcs = m->step_dcs; s.dpe = m->step_dpe;
   s.g_h_init = m->grads + L.h_init; s.g_c_init = m->grads + L.c_init; s.g_peep = m->grads + L.peep;
   const dim3 grid(cdiv(B, STEP_BN), cdiv(H, 128), 1);

@@ -47,6 +47,7 @@ struct ScanArgs {
   float* dXg; float* dac;
   float* g_h_init; float* g_c_init; float* g_peep; float* g_b;
   float clip;
+  int relu;            // vanilla cell: rectifier instead of tanh (dense-input layers)
   int b_split;                   // GRU: k >= 2H of da comes from dac (tmB2)
   long long* dbg;                // optional clock64 phase sums of CTA (0,0,0) (SBR_SCAN_TIMELINE)
   int fence_mode;                // publication fences (SBR_SCAN_FENCE, experiments): see publish_step()
@@ -295,7 +296,8 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
             hreg[j] = (1.f - uu) * hreg[j] + uu * cand;
             sv[0][j] = r; sv[1][j] = uu; sv[2][j] = cand; sv[3][j] = ac;
           } else {
-            hreg[j] = tanh_fast(xg[0][j] + pre[j]);
+            const float z = xg[0][j] + pre[j];
+            hreg[j] = a.relu ? fmaxf(z, 0.f) : tanh_fast(z);
           }
         }
         st8(a.hs + ((long long)(t + 1) * B + b) * H + u0, hreg);
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd_kernel(const __grid_cons
                 carry_new = d * (1.f - uu);
               } else {
                 const float h_new = sv[q][0];
-                dx[0] = clip_sym(d * (1.f - h_new * h_new), a.clip);
+                dx[0] = clip_sym(d * (a.relu ? (h_new > 0.f ? 1.f : 0.f) : 1.f - h_new * h_new), a.clip);
                 carry_new = 0.f;
               }
             }
@@ -883,7 +885,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd2_kernel(const __grid_con
                   carry_new = d * (1.f - uu);
                 } else {
                   const float h_new = sv[q][0];
-                  dx[0] = clip_sym(d * (1.f - h_new * h_new), a.clip);
+                  dx[0] = clip_sym(d * (a.relu ? (h_new > 0.f ? 1.f : 0.f) : 1.f - h_new * h_new), a.clip);
                   carry_new = 0.f;
                 }
               }
@@ -1125,6 +1127,7 @@ int launch_rnn_forward_persistent(sbr_model* m, const LayerDesc& L, const int32_
   a.fence_mode = m->scan_fence_mode;
   a.dbg = scan_dbg_buffer(m);
   a.B = B; a.H = H; a.G = G; a.t_max = t_max; a.n_chunks = cdiv(H, SC_KC);
+  a.relu = L.relu;
   a.len = len; a.peep = m->params + L.peep; a.Xg = L.Xg; a.hs = L.hs; a.cs = L.cs; a.act = L.act;
   const int unit_ctas = cdiv(H, SC_U), n_tiles = cdiv(B, 128);
   if (unit_ctas > m->n_sm) return 1;
@@ -1175,6 +1178,7 @@ int launch_rnn_backward_persistent(sbr_model* m, const LayerDesc& L, const int32
   a.fence_mode = m->scan_fence_mode;
   a.dbg = scan_dbg_buffer(m);
   a.B = B; a.H = H; a.G = G; a.t_max = t_max; a.n_chunks = cdiv(GH, SC_KC);
+  a.relu = L.relu;
   a.len = len; a.peep = m->params + L.peep;
   a.act_r = L.act; a.cs_r = L.cs; a.hs_r = L.hs; a.dhs = dh_last ? nullptr : L.dhs; a.dh_last = dh_last;
   a.dXg = L.dXg; a.dac = L.dac; a.clip = m->cfg.grad_clip; a.b_split = 2 * H;

@@ -43,7 +43,5 @@ class RecurrentLayers(object):
         self.name = name
 
     def engine_kwargs(self):
-        if self.bidirectional:
-            raise NotImplementedError("bidirectional layers (--r_bi) are outside the B200 hot path (SURVEY.md §8f rank 3)")
         return dict(cell=self.layer_type, layers=tuple(self.layers), embedding=max(0, self.embedding_size),
-                    grad_clip=float(self.grad_clip))
+                    grad_clip=float(self.grad_clip), bidirectional=bool(self.bidirectional))

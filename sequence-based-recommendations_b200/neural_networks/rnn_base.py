@@ -198,6 +198,10 @@ class RNNBase(object):
             elif name == "out.W":
                 a = float(self.last_layer_init) * np.sqrt(6.0 / (shape[0] + shape[1]))
                 v = rng.uniform(-a, a, size=shape)
+            elif leaf in ("W_in_to_hid", "W_hid_to_hid"):
+                # Vanilla layers with a dense input are lasagne.layers.RecurrentLayer (recurrent_layers.py:98-99),
+                # whose weights default to lasagne.init.Uniform() = U(-0.01, 0.01)
+                v = rng.uniform(-0.01, 0.01, size=shape)
             elif leaf.startswith("W_"):
                 v = rng.normal(0.0, 0.1, size=shape)
             else:

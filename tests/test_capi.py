@@ -24,7 +24,7 @@ def test_build_entry_point_and_symbols():
     for s in syms:
         assert hasattr(lib, s), "library does not export " + s
     assert sorted(_capi.SIGNATURES) == syms, "ctypes table and header disagree"
-    assert lib.sbr_abi_version() == 1
+    assert lib.sbr_abi_version() == 2
 
 
 def test_config_struct_matches_header_layout(tmp_path):

@@ -101,7 +101,7 @@ def test_world_size_2_gradient_identity_and_sharding(tmp_path):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=400) for _ in procs]     # a cold `import torch` in the spawned ranks can take minutes
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

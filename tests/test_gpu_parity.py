@@ -18,7 +18,7 @@ def _engine(spec, B, T, **kw):
     args = dict(n_items=spec.n_items, cell=spec.cell, layers=spec.layers, loss=spec.loss, max_length=T,
                 batch_size=B, embedding=spec.embedding, n_extra_ids=spec.n_extra_ids,
                 ids_per_step=spec.ids_per_step, grad_clip=spec.grad_clip, regularization=spec.regularization,
-                last_layer_tanh=spec.last_layer_tanh)
+                last_layer_tanh=spec.last_layer_tanh, bidirectional=spec.bidirectional)
     args.update(kw)
     return _capi.Engine(**args)
 
@@ -142,6 +142,34 @@ def test_cce_gradients_wide_layer_global_weights(cell):
 def test_stacked_layers(cell, layers):
     spec = O.Spec(n_items=150, cell=cell, layers=layers, loss="CCE", regularization=-0.02)
     check_grads(spec, B=13, T=8, seed=1)
+
+
+@pytest.mark.parametrize("cell,layers,B", [("GRU", (40,), 11), ("LSTM", (32,), 11), ("Vanilla", (48,), 16),
+                                           ("GRU", (40, 24), 11), ("LSTM", (24, 40, 16), 16), ("LSTM", (200,), 32),
+                                           ("GRU", (256,), 64)])
+def test_bidirectional_stacks(cell, layers, B):
+    """--r_bi (recurrent_layers.py:72-78): every depth is a forward and a backwards layer over the same input, outputs
+    concatenated; the final state is [forward state after the last item | backward state after the first item]."""
+    spec = O.Spec(n_items=211, cell=cell, layers=layers, loss="CCE", bidirectional=True)
+    check_grads(spec, B=B, T=9)
+
+
+@pytest.mark.parametrize("layers,emb,bi,B", [((48, 32), 0, False, 11), ((40,), 12, False, 16), ((32, 24, 16), 0, True, 16),
+                                            ((256, 64), 0, False, 32), ((200, 100), 0, False, 128)])
+def test_dense_vanilla_layers(layers, emb, bi, B):
+    """Vanilla layers fed by a dense input are Lasagne RecurrentLayers (recurrent_layers.py:98-99): rectifier, parameters
+    listed hid_init, W_in_to_hid, b, W_hid_to_hid; layer 0 without an embedding stays the in-tree tanh cell."""
+    spec = O.Spec(n_items=211, cell="Vanilla", layers=layers, embedding=emb, loss="CCE", bidirectional=bi)
+    check_grads(spec, B=B, T=9)
+
+
+def test_bidirectional_embedding_and_sampling_loss():
+    spec = O.Spec(n_items=150, cell="GRU", layers=(32, 16), loss="CCE", embedding=12, bidirectional=True)
+    check_grads(spec, B=8, T=7)
+    spec = O.Spec(n_items=150, cell="LSTM", layers=(32,), loss="TOP1", bidirectional=True)
+    check_grads(spec, B=8, T=7)
+    spec = O.Spec(n_items=101, cell="GRU", layers=(24,), loss="CCE", n_extra_ids=10, ids_per_step=2, bidirectional=True)
+    check_grads(spec, B=9, T=6, K=2)
 
 
 @pytest.mark.parametrize("cell", ["GRU", "LSTM"])

@@ -221,3 +221,59 @@ def test_margin_targets_match_reference_fill():
     w = 2.0 * 2 / (10 - 2 - 3)
     assert W[0, 0] == w and W[0, 4] == -1 and W[0, 1] == 0
     assert Y[0, 4] == 1 and Y[0, 1] == 0 and Y[0, 0] == 0
+
+
+@pytest.mark.parametrize("cell,layers,emb", [("GRU", (4,), 0), ("LSTM", (4, 3), 0), ("GRU", (3, 3), 3), ("Vanilla", (5,), 0)])
+def test_bidirectional_gradients(cell, layers, emb):
+    """--r_bi (recurrent_layers.py:72-78): forward + backwards layer per depth, concatenated; finite differences."""
+    spec = O.Spec(n_items=9, cell=cell, layers=layers, embedding=emb, loss="CCE", bidirectional=True)
+    names = [n for n, _ in O.param_names_shapes(spec)]
+    assert "l0b.hid_init" in names and names.index("l0.hid_init") < names.index("l0b.W_in_to_" + ("ingate" if cell == "LSTM" else ("updategate" if cell == "GRU" else "hidden_update")))
+    assert dict(O.param_names_shapes(spec))["out.W"] == (2 * layers[-1], 9)
+    assert fd_check(spec, seed=6, B=3, T=5) < 2e-5
+
+
+@pytest.mark.parametrize("layers,emb,bi", [((5, 4), 0, False), ((4,), 3, False), ((4, 3, 3), 0, True)])
+def test_dense_vanilla_layers(layers, emb, bi):
+    """Vanilla layers with a dense input are Lasagne RecurrentLayers (recurrent_layers.py:98-99): rectifier, parameter
+    order hid_init, W_in_to_hid, b, W_hid_to_hid, Uniform(-0.01, 0.01) weights; layer 0 without embedding stays the
+    in-tree tanh copy."""
+    spec = O.Spec(n_items=9, cell="Vanilla", layers=layers, embedding=emb, loss="CCE", bidirectional=bi)
+    names = [n for n, _ in O.param_names_shapes(spec)]
+    first_dense = "l0." if emb else "l1."
+    i = names.index(first_dense + "hid_init")
+    assert names[i:i + 4] == [first_dense + x for x in ("hid_init", "W_in_to_hid", "b", "W_hid_to_hid")]
+    if not emb:
+        assert "l0.W_in_to_hidden_update" in names and O.dense_vanilla(spec, 0) is False
+    vals = O.init_params(spec, np.random.RandomState(0))
+    W = dict(zip(names, vals))[first_dense + "W_hid_to_hid"]
+    assert np.abs(W).max() <= 0.01 and W.std() > 0.004
+    assert fd_check(spec, seed=8, B=3, T=5) < 2e-5
+
+
+def test_backwards_layer_equals_forward_layer_on_reversed_rows():
+    """A backwards layer over left-aligned, right-padded rows computes exactly what a forward layer computes on the rows
+    with their valid prefix reversed; its output, un-reversed the same way, is the aligned output.  (This identity is
+    how the CUDA path runs bidirectional stacks on its forward-only scan kernels.)"""
+    rng = np.random.RandomState(3)
+    spec = O.Spec(n_items=12, cell="LSTM", layers=(5,), loss="CCE")
+    vals = O.init_params(spec, rng)
+    for v in vals:
+        if not v.any():
+            v[...] = rng.normal(0, 0.1, size=v.shape)
+    P = O.as_dict(spec, vals)
+    X, mask, lens = make_batch(rng, 4, 6, 12)
+    T = X.shape[1]
+    maskT = mask.T
+    W_in, _, b, _ = O._stack(spec, P, 0)
+    Xt = np.transpose(X, (1, 0, 2))
+    Xg = W_in[Xt, :].sum(axis=-2) + b
+    hs_b, _ = O._layer_forward(spec, 0, P, Xg, maskT, backwards=True)
+    Xr = np.zeros_like(X)
+    for i in range(X.shape[0]):
+        Xr[i, :lens[i]] = X[i, :lens[i]][::-1]
+    Xgr = W_in[np.transpose(Xr, (1, 0, 2)), :].sum(axis=-2) + b
+    hs_f, _ = O._layer_forward(spec, 0, P, Xgr, maskT, backwards=False)
+    for i in range(X.shape[0]):
+        np.testing.assert_allclose(hs_b[:lens[i], i], hs_f[:lens[i], i][::-1], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(hs_b[0, i], hs_f[lens[i] - 1, i], rtol=0, atol=1e-15)      # final state of the backwards scan
