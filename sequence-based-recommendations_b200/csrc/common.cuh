@@ -132,6 +132,7 @@ struct sbr_model {
   float* emb_out = nullptr;   // [T*B, K*E]
   float* demb = nullptr;
   // bidirectional stacks: the backwards layers run the forward-only scan kernels on rows whose valid prefix is reversed
+  int* wg_list = nullptr; int wg_list_rows = 0;   // wgrad_tc: [1 + T*B/32] stages of the contraction holding valid rows (this batch)
   int32_t* X_rev = nullptr;   // [B, T, K] ids with every row's valid prefix reversed
   float* emb_out_rv = nullptr; float* demb_rv = nullptr;       // embedding path in reversed coordinates
   float* cat_al = nullptr;    // [T*B, 2*maxH] level output [forward | backward] aligned with the input positions
@@ -237,6 +238,7 @@ int launch_rnn_backward_tc(sbr_model* m, const LayerDesc& L, const int32_t* len,
 int tc_scan_applies(int G, int H);   // 1 when both tcgen05 scans handle this layer shape
 
 // wgrad_tc.cu : dW_hid[H, G*H] += sum_rows h_prev[row]^T da[row] on tcgen05 (3xTF32) from the K-major copies
+int launch_wgrad_stage_list(sbr_model* m, const int32_t* len, int B, int rows);
 int launch_wgrad_tc(sbr_model* m, const LayerDesc& L, int rows, float* dW, int ldw);
 
 // tc_gemm.cu : the same product on tcgen05 (3xTF32, operands split on the fly); returns 1 when it does not apply

@@ -263,7 +263,7 @@ extern "C" void sbr_destroy(sbr_model* m) {
   F(m->params); F(m->grads); F(m->opt_a); F(m->opt_b);
   for (LayerDesc& L : m->layers) { F(L.Xg); F(L.act); F(L.hs); F(L.cs); F(L.dXg); F(L.dac); F(L.dhs); F(L.hT); F(L.aT); }
   for (BatchSlot& s : m->slots) { F(s.X); F(s.len); F(s.Y); F(s.pop); }
-  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe); F(m->scan_sync); F(m->ds_off); F(m->ds_ids); F(m->ds_rows); F(m->X_rev); F(m->emb_out_rv); F(m->demb_rv); F(m->cat_al); F(m->cat_rv); F(m->dcat_al); F(m->dcat_rv); F(m->h_last_dir); F(m->dh_last_dir);
+  F(m->emb_out); F(m->demb); F(m->h_last); F(m->dh_last); F(m->logits); F(m->row_loss); F(m->WhidT); F(m->step_carry); F(m->step_dcs); F(m->step_dpe); F(m->scan_sync); F(m->ds_off); F(m->ds_ids); F(m->ds_rows); F(m->wg_list); F(m->X_rev); F(m->emb_out_rv); F(m->demb_rv); F(m->cat_al); F(m->cat_rv); F(m->dcat_al); F(m->dcat_rv); F(m->h_last_dir); F(m->dh_last_dir);
   F(m->mY); F(m->mW); F(m->cells); F(m->Wc); F(m->dWc); F(m->bc);
   F(m->tgt_off); F(m->tgt_ids); F(m->w_neg); F(m->def_tgt); F(m->excl_off); F(m->excl_ids); F(m->topk_ids);
   if (m->h_len) cudaFreeHost(m->h_len);
@@ -383,6 +383,7 @@ static int create_impl(sbr_model* m) {
   }
   if ((rc = dev_alloc(m, &m->h_last, B * m->H_last))) return rc;
   if ((rc = dev_alloc(m, &m->dh_last, B * m->H_last))) return rc;
+  if ((rc = dev_alloc(m, &m->wg_list, 2 + TB / 32))) return rc;
   if (m->nd == 2) {
     size_t maxH = 0;
     for (const LayerDesc& L : m->layers) maxH = std::max<size_t>(maxH, L.H);
@@ -817,6 +818,7 @@ static int backward_stack(sbr_model* m, const BatchSlot& s) {
     CU_TRY(m, cudaMemcpy2DAsync(m->dh_last_dir + (size_t)B * H, (size_t)H * sizeof(float), m->dh_last + H, (size_t)2 * H * sizeof(float),
                                 (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, m->stream));
   }
+  if ((rc = launch_wgrad_stage_list(m, s.len, B, rows))) return rc;
   for (int li = m->L - 1; li >= 0; --li) {
     for (int dir = 0; dir < nd; ++dir) {
       LayerDesc& L = m->layers[li * nd + dir];

@@ -287,18 +287,28 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const __grid_cons
     const bool want_lo = warp >= 4;
     const float* src = a.W_hidT + (int64_t)(g * H + j0 + j) * H;   // k contiguous
     const uint32_t dst = (want_lo ? tAlo : tAhi) + lane_off;
-    for (int k0 = 0; k0 < Kp; k0 += 8) {
-      uint32_t r[8];
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;      // H % 4 == 0: 16-byte loads, guarded per quad
-      if (live && k0 < H) v0 = __ldg(reinterpret_cast<const float4*>(src + k0));
-      if (live && k0 + 4 < H) v1 = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
-      const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    // 8 independent 16-byte loads in flight per thread (the row comes from L2 / HBM: with one load per round trip this
+    // prologue took 15 000 cycles = 8 us per launch)
+    for (int kb = 0; kb < Kp; kb += 32) {
+      float4 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float h = tf32_hi(vv[i]);
-        r[i] = __float_as_uint(want_lo ? vv[i] - h : h);
+      for (int q = 0; q < 8; ++q) {
+        const int k = kb + 4 * q;
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);                   // H % 4 == 0: 16-byte loads, guarded per quad
+        if (live && k < H) v[q] = __ldg(reinterpret_cast<const float4*>(src + k));
       }
-      tmem_st8(dst + k0, r);
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) {
+        if (kb + 4 * q >= Kp) break;
+        const float vv[8] = {v[q].x, v[q].y, v[q].z, v[q].w, v[q + 1].x, v[q + 1].y, v[q + 1].z, v[q + 1].w};
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = tf32_hi(vv[i]);
+          r[i] = __float_as_uint(want_lo ? vv[i] - h : h);
+        }
+        tmem_st8(dst + kb + 4 * q, r);
+      }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
@@ -639,14 +649,23 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
       const int k = mt * 128 + quad * 32 + (tid & 31);
       const float* src = a.W_hid + (int64_t)k * GH + j0;
       const uint32_t dst = tmem + 32 * MT + mt * 2 * Kb + (want_lo ? Kb : 0) + lane_off;
-      for (int c0 = 0; c0 < Kb; c0 += 16) {                       // 4 units x 4 gates per pass
-        const int jb = c0 >> 2;
-        float4 vg[4];
+      for (int cb = 0; cb < Kb; cb += 32) {                       // two passes of 4 units x 4 gates: 8 loads in flight
+       float4 vgs[2][4];
+#pragma unroll
+       for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          vg[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < H && g < G && jb < nj) vg[g] = __ldg(reinterpret_cast<const float4*>(src + g * H + jb));   // nj % 4 == 0
+          const int jb = (cb + 16 * h2) >> 2;
+          vgs[h2][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < H && g < G && jb < nj) vgs[h2][g] = __ldg(reinterpret_cast<const float4*>(src + g * H + jb));   // nj % 4 == 0
         }
+#pragma unroll
+       for (int h2 = 0; h2 < 2; ++h2) {
+        const int c0 = cb + 16 * h2;
+        if (c0 >= Kb) break;
+        float4 vg[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) vg[g] = vgs[h2][g];
         uint32_t r0[8], r1[8];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -660,6 +679,7 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
         }
         tmem_st8(dst + c0, r0);
         if (c0 + 8 < Kb) tmem_st8(dst + c0 + 8, r1);
+       }
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -50,6 +50,7 @@ struct ScanArgs {
   int relu;            // vanilla cell: rectifier instead of tanh (dense-input layers)
   int b_split;                   // GRU: k >= 2H of da comes from dac (tmB2)
   long long* dbg;                // optional clock64 phase sums of CTA (0,0,0) (SBR_SCAN_TIMELINE)
+  int acq_spin;                  // experiments (SBR_SCAN_ACQ_SPIN): acquire loads in the counter spin / cluster-acquire barrier waits, as before
   int fence_mode;                // publication fences (SBR_SCAN_FENCE, experiments): see publish_step()
   int tile0;                     // first batch tile of this launch (large batches run as several launches over tile slices)
 };
@@ -58,6 +59,13 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+// Spin on a step counter: relaxed polls, ONE acquire fence once the value is there (an acquire load per poll drags an
+// L1 invalidation -- CCTL.IVALL -- behind every iteration of the spin)
+__device__ __forceinline__ void wait_counter_gpu(const unsigned int* p, unsigned int need) {
+  unsigned int v;
+  do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); } while (v < need);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void red_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_fwd_kernel(const __grid_cons
         const long long w0 = a.dbg ? clock64() : 0;
         if (t > 0) {
           const unsigned int need = (unsigned int)t * (unsigned int)group_ctas;
-          while (ld_acquire_gpu(ctr) < need) { }
+          if (a.acq_spin) { while (ld_acquire_gpu(ctr) < need) { } } else wait_counter_gpu(ctr, need);
           fence_proxy_async_all();
         }
         if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[8] += clock64() - w0;
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd_kernel(const __grid_cons
       for (int s = 1; s < n_steps; ++s) {
         const int t = t_end - 1 - s;
         const unsigned int need = (unsigned int)s * (unsigned int)group_ctas;
-        while (ld_acquire_gpu(ctr) < need) { }
+        if (a.acq_spin) { while (ld_acquire_gpu(ctr) < need) { } } else wait_counter_gpu(ctr, need);
         fence_proxy_async_all();
         for (int c = 0; c < NC; ++c, ++gc) {
           const int rs = gc % SC_LOOKB;
@@ -827,7 +835,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd2_kernel(const __grid_con
         if (NC > 0) ++n_done;
         SC_ACC(2);
         // the other ranks' partials of my rows
-        mbar_wait_cluster(&recv_full[buf], ((s - 1) >> 1) & 1);
+        if (a.acq_spin) mbar_wait_cluster(&recv_full[buf], ((s - 1) >> 1) & 1); else mbar_wait(&recv_full[buf], ((s - 1) >> 1) & 1);   // bulk-copy complete_tx: no cluster acquire needed
         SC_ACC(3);
         if (tid == 0) mbar_arrive_expect_tx(&recv_full[buf], (SC_KS - 1) * slice_bytes);     // next use of this buffer (two steps later)
 #pragma unroll
@@ -980,7 +988,7 @@ __global__ void __launch_bounds__(SC_NT, 1) tc_scan_bwd2_kernel(const __grid_con
         const long long w0 = a.dbg ? clock64() : 0;
         if (NC > 0) {
           const unsigned int need = (unsigned int)s * (unsigned int)group_ctas;
-          while (ld_acquire_gpu(ctr) < need) { }
+          if (a.acq_spin) { while (ld_acquire_gpu(ctr) < need) { } } else wait_counter_gpu(ctr, need);
           fence_proxy_async_all();
         }
         if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[26] += clock64() - w0;
@@ -1125,6 +1133,7 @@ int launch_rnn_forward_persistent(sbr_model* m, const LayerDesc& L, const int32_
   }
   ScanArgs a{};
   a.fence_mode = m->scan_fence_mode;
+  a.acq_spin = getenv("SBR_SCAN_ACQ_SPIN") ? 1 : 0;
   a.dbg = scan_dbg_buffer(m);
   a.B = B; a.H = H; a.G = G; a.t_max = t_max; a.n_chunks = cdiv(H, SC_KC);
   a.relu = L.relu;
@@ -1176,6 +1185,7 @@ int launch_rnn_backward_persistent(sbr_model* m, const LayerDesc& L, const int32
   const int H = L.H, G = L.G, GH = G * H;
   ScanArgs a{};
   a.fence_mode = m->scan_fence_mode;
+  a.acq_spin = getenv("SBR_SCAN_ACQ_SPIN") ? 1 : 0;
   a.dbg = scan_dbg_buffer(m);
   a.B = B; a.H = H; a.G = G; a.t_max = t_max; a.n_chunks = cdiv(GH, SC_KC);
   a.relu = L.relu;

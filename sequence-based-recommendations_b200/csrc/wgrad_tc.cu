@@ -76,8 +76,22 @@ struct WgArgs {
   float* dW;
   int ldw, H, GH;
   int rq_total;      // row-quads of K (rows / 4), even
-  int rq_per_split;  // multiple of WG_QPS
+  const int* list;   // list[0] = n, list[1..n] = the stages (32 consecutive rows of K) that hold at least one valid row
 };
+
+// Stages of the contraction worth visiting.  The scans write exact zeros into aT for masked (t, b) rows, so a stage
+// whose 32 rows are all beyond their sequences contributes nothing: with the nested-prefix batches of the reference
+// (mean length ~ a third of max_length) that is most of K.  Order does not matter for a sum.
+__global__ void wgrad_stage_list_kernel(const int32_t* __restrict__ len, int B, int rows, int* __restrict__ list) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s * 32 >= rows) return;
+  bool any = false;
+  for (int r = s * 32; r < min(rows, s * 32 + 32) && !any; ++r) {
+    const int t = r / B, b = r - t * B;
+    any = t < len[b];
+  }
+  if (any) list[1 + atomicAdd(list, 1)] = s;
+}
 
 __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const WgArgs a) {
   extern __shared__ __align__(1024) uint8_t wg_smem[];
@@ -88,9 +102,12 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const WgArgs a) {
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nt = blockIdx.x, mt = blockIdx.y;
-  const int rq0 = blockIdx.z * a.rq_per_split;
-  const int rq1 = min(a.rq_total, rq0 + a.rq_per_split);
-  const int n_stages = (rq1 - rq0 + WG_QPS - 1) / WG_QPS;
+  // this CTA's share of the stage list
+  const int n_list = a.list[0];
+  const int per = (n_list + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int i0 = min(n_list, (int)blockIdx.z * per);
+  const int n_stages = min(n_list, i0 + per) - i0;
+  const int* stages = a.list + 1 + i0;
 
   if (tid == 0) {
     for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -115,8 +132,8 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const WgArgs a) {
         for (int i = 0; i < n_stages; ++i) {
           const int s = i % WG_STAGES;
           if (i >= WG_STAGES) mbar_wait(&empty[s], ((i / WG_STAGES) - 1) & 1);
-          const int rq = rq0 + i * WG_QPS;
-          const int nq = min(WG_QPS, rq1 - rq);
+          const int rq = __ldg(stages + i) * WG_QPS;
+          const int nq = min(WG_QPS, a.rq_total - rq);
           const uint32_t bytes = (uint32_t)nq * 128 * 16;
           uint8_t* st = wg_smem + (size_t)s * 4 * WG_PART_BYTES;
           mbar_arrive_expect_tx(&full[s], 4 * bytes);
@@ -137,8 +154,8 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const WgArgs a) {
           const int s = i % WG_STAGES;
           mbar_wait(&full[s], (i / WG_STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int rq = rq0 + i * WG_QPS;
-          const int nq = min(WG_QPS, rq1 - rq);
+          const int rq = __ldg(stages + i) * WG_QPS;
+          const int nq = min(WG_QPS, a.rq_total - rq);
           const uint32_t base = smem_u32(wg_smem + (size_t)s * 4 * WG_PART_BYTES);
           for (int kc = 0; kc < nq / 2; ++kc) {     // one MMA k-chunk = 8 rows = 2 row-quads = 4 KB
             const uint32_t o = (uint32_t)kc * 4096;
@@ -204,11 +221,13 @@ int launch_wgrad_tc(sbr_model* m, const LayerDesc& L, int rows, float* dW, int l
   a.hT_part = L.hT_part; a.hT_tile = L.hT_tile; a.aT_part = L.aT_part; a.aT_tile = L.aT_tile;
   a.dW = dW; a.ldw = ldw; a.H = L.H; a.GH = L.G * L.H;
   a.rq_total = rows / 4;
+  if (!m->wg_list || m->wg_list_rows != rows) {
+    sbr_set_error(m, SBR_E_ARG, "wgrad_tc: the stage list of this batch is missing");
+    return SBR_E_ARG;
+  }
+  a.list = m->wg_list;
   const int mts = cdiv(L.H, 128), nts = cdiv(L.G * L.H, 128);
-  int splits = std::max(1, m->n_sm / (mts * nts));
-  int per = (int)round_up(cdiv(a.rq_total, splits), WG_QPS);
-  splits = cdiv(a.rq_total, per);
-  a.rq_per_split = per;
+  const int splits = std::max(1, std::min(m->n_sm / (mts * nts), cdiv(rows, 32)));
   const size_t smem = (size_t)WG_STAGES * 4 * WG_PART_BYTES + 1024;
   static std::vector<int> attr_devs;      // the opt-in shared-memory limit is a per-device attribute
   if (std::find(attr_devs.begin(), attr_devs.end(), m->dev) == attr_devs.end()) {
@@ -218,5 +237,17 @@ int launch_wgrad_tc(sbr_model* m, const LayerDesc& L, int rows, float* dW, int l
   }
   wgrad_tc_kernel<<<dim3(nts, mts, splits), WG_NT, smem, m->stream>>>(a);
   KERNEL_CHECK(m);
+  return 0;
+}
+
+// once per batch (every layer of the stack shares the lengths): which 32-row stages of K = t_max * B hold valid rows
+int launch_wgrad_stage_list(sbr_model* m, const int32_t* len, int B, int rows) {
+  m->wg_list_rows = 0;
+  if (!m->wg_list || rows <= 0) return 0;
+  CU_TRY(m, cudaMemsetAsync(m->wg_list, 0, sizeof(int), m->stream));
+  const int n = cdiv(rows, 32);
+  wgrad_stage_list_kernel<<<cdiv(n, 128), 128, 0, m->stream>>>(len, B, rows, m->wg_list);
+  KERNEL_CHECK(m);
+  m->wg_list_rows = rows;
   return 0;
 }

@@ -30,6 +30,8 @@ def gemm():
     ]
     out = []
     for name, ta, tb, M, N, K in shapes:
+        if len(sys.argv) > 2 and not any(name.startswith(c) for c in sys.argv[2].split(",")):
+            continue
         A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
         B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
         reps = 5
@@ -45,7 +47,9 @@ def gemm():
 
 def scan():
     rng = np.random.RandomState(1)
-    for name, cell, layers, B, T, N in [("c3 LSTM 2x256 B512 T200", "LSTM", (256, 256), 512, 200, 2000),
+    for name, cell, layers, B, T, N in [("c2 LSTM 1x200 B128 T200", "LSTM", (200,), 128, 200, 3706),
+                                        ("c2g GRU 1x200 B128 T200", "GRU", (200,), 128, 200, 3706),
+                                        ("c3 LSTM 2x256 B512 T200", "LSTM", (256, 256), 512, 200, 2000),
                                         ("c4-shard LSTM 1x512 B256 T200", "LSTM", (512,), 256, 200, 2000),
                                         ("c5-shard GRU 2x512 B256 T500", "GRU", (512, 512), 256, 500, 2000)]:
         envs = [{}, {"SBR_DISABLE_STEP_SCAN": "1"}]
@@ -54,7 +58,8 @@ def scan():
         if len(sys.argv) > 3:
             envs = [dict(kv.split("=") for kv in e.split(",")) if e != "-" else {} for e in sys.argv[3:]]
         for env in envs:
-            for k in ("SBR_DISABLE_STEP_SCAN", "SBR_SCAN_FENCE", "SBR_DISABLE_PERSISTENT_SCAN", "SBR_DISABLE_SPLITK_SCAN"):
+            for k in ("SBR_DISABLE_STEP_SCAN", "SBR_SCAN_FENCE", "SBR_DISABLE_PERSISTENT_SCAN", "SBR_DISABLE_SPLITK_SCAN",
+                      "SBR_TC_EXPERIMENT"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             e = _capi.Engine(n_items=N, cell=cell, layers=layers, max_length=T, batch_size=B)
