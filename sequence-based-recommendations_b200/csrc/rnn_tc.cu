@@ -279,17 +279,18 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const __grid_cons
   const uint32_t tAlo = tmem + 64 + Kp;     // Kp columns (64 + 2*Kp <= 512)
 
   // ---- A operand: row m = 4*j + g  <->  W_hid[:, g*H + j0 + j]; K along the TMEM columns.
-  //      warps 0-3 stage the hi copy, warps 4-7 the lo copy (same lane quadrants)
+  //      A thread reads ITS row (a warp request touches 32 rows = 32 sectors: the prologue is bound by sector
+  //      requests, 13 000 cycles when every row was read twice), so each word is loaded once: warps 0-3 stage the
+  //      first half of K, warps 4-7 the second (same lane quadrants), hi and lo copies from the same registers;
+  //      8 independent 16-byte loads in flight per thread.
   {
     const int m = quad * 32 + (tid & 31);
     const int j = m >> 2, g = m & 3;
     const bool live = (g < G) && (j < nj);
-    const bool want_lo = warp >= 4;
     const float* src = a.W_hidT + (int64_t)(g * H + j0 + j) * H;   // k contiguous
-    const uint32_t dst = (want_lo ? tAlo : tAhi) + lane_off;
-    // 8 independent 16-byte loads in flight per thread (the row comes from L2 / HBM: with one load per round trip this
-    // prologue took 15 000 cycles = 8 us per launch)
-    for (int kb = 0; kb < Kp; kb += 32) {
+    const int kmid = min(Kp, ((Kp / 2 + 31) / 32) * 32);
+    const int kb0 = warp >= 4 ? kmid : 0, kb1 = warp >= 4 ? Kp : kmid;
+    for (int kb = kb0; kb < kb1; kb += 32) {
       float4 v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -301,13 +302,15 @@ __global__ void __launch_bounds__(FWD_NT, 1) rnn_fwd_tc_kernel(const __grid_cons
       for (int q = 0; q < 8; q += 2) {
         if (kb + 4 * q >= Kp) break;
         const float vv[8] = {v[q].x, v[q].y, v[q].z, v[q].w, v[q + 1].x, v[q + 1].y, v[q + 1].z, v[q + 1].w};
-        uint32_t r[8];
+        uint32_t rh[8], rl[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float h = tf32_hi(vv[i]);
-          r[i] = __float_as_uint(want_lo ? vv[i] - h : h);
+          rh[i] = __float_as_uint(h);
+          rl[i] = __float_as_uint(vv[i] - h);
         }
-        tmem_st8(dst + kb + 4 * q, r);
+        tmem_st8(tAhi + lane_off + kb + 4 * q, rh);
+        tmem_st8(tAlo + lane_off + kb + 4 * q, rl);
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -642,14 +645,16 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
   const uint32_t tmem = tmem_base_s;
 
   // ---- A operand tiles: row = hidden index k, column kk = 4*j + g  <->  W_hid[k][g*H + j0 + j]
-  //      warps 0-3 stage the hi copies, warps 4-7 the lo copies
+  //      every word is loaded once: warps 0-3 stage the first half of the columns, warps 4-7 the second, hi and lo
+  //      copies from the same registers (the prologue is bound by sector requests: a warp request = 32 rows)
   {
-    const bool want_lo = warp >= 4;
+    const int cmid = min(Kb, ((Kb / 2 + 31) / 32) * 32);
+    const int cb0 = warp >= 4 ? cmid : 0, cb1 = warp >= 4 ? Kb : cmid;
     for (int mt = 0; mt < MT; ++mt) {
       const int k = mt * 128 + quad * 32 + (tid & 31);
       const float* src = a.W_hid + (int64_t)k * GH + j0;
-      const uint32_t dst = tmem + 32 * MT + mt * 2 * Kb + (want_lo ? Kb : 0) + lane_off;
-      for (int cb = 0; cb < Kb; cb += 32) {                       // two passes of 4 units x 4 gates: 8 loads in flight
+      const uint32_t dst = tmem + 32 * MT + mt * 2 * Kb + lane_off;
+      for (int cb = cb0; cb < cb1; cb += 32) {                    // two passes of 4 units x 4 gates: 8 loads in flight
        float4 vgs[2][4];
 #pragma unroll
        for (int h2 = 0; h2 < 2; ++h2)
@@ -666,19 +671,20 @@ __global__ void __launch_bounds__(bwd_threads(BT), 1) rnn_bwd_tc_kernel(const __
         float4 vg[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) vg[g] = vgs[h2][g];
-        uint32_t r0[8], r1[8];
+        uint32_t r0[8], r1[8], l0[8], l1[8];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const float u4[4] = {vg[g].x, vg[g].y, vg[g].z, vg[g].w};
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const float h = tf32_hi(u4[jj]);
-            const uint32_t bits = __float_as_uint(want_lo ? u4[jj] - h : h);
-            if (jj < 2) r0[4 * jj + g] = bits; else r1[4 * (jj - 2) + g] = bits;
+            const uint32_t hb = __float_as_uint(h), lb = __float_as_uint(u4[jj] - h);
+            if (jj < 2) { r0[4 * jj + g] = hb; l0[4 * jj + g] = lb; } else { r1[4 * (jj - 2) + g] = hb; l1[4 * (jj - 2) + g] = lb; }
           }
         }
         tmem_st8(dst + c0, r0);
-        if (c0 + 8 < Kb) tmem_st8(dst + c0 + 8, r1);
+        tmem_st8(dst + Kb + c0, l0);
+        if (c0 + 8 < Kb) { tmem_st8(dst + c0 + 8, r1); tmem_st8(dst + Kb + c0 + 8, l1); }
        }
       }
     }

@@ -169,9 +169,10 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
   const uint32_t rawA_bytes = 128u * TG_KC * 4u, rawB_bytes = (uint32_t)BN * TG_KC * 4u;
   uint8_t* rawA0 = tg_base + (size_t)TG_STAGES * stage_bytes;
   uint8_t* rawB0 = rawA0 + (size_t)LOOK * rawA_bytes;
+  const int bn_shift = 31 - __clz(BN);
   auto b_coords = [&](int idx, int& n, int& kq) {
     if (a.b_mode == 0) { n = ((idx >> 6) << 3) + (idx & 7); kq = (idx >> 3) & 7; }
-    else { kq = idx / BN; n = idx - kq * BN; }
+    else { kq = idx >> bn_shift; n = idx & (BN - 1); }       // BN is a power of two (an integer division here cost more than the conversion)
   };
 
   if (warp < 4) {
