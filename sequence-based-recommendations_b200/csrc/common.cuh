@@ -132,6 +132,7 @@ struct sbr_model {
   float* emb_out = nullptr;   // [T*B, K*E]
   float* demb = nullptr;
   // bidirectional stacks: the backwards layers run the forward-only scan kernels on rows whose valid prefix is reversed
+  bool on_side = false;     // launchers are currently enqueuing on the side stream (work that overlaps a cluster scan)
   int* wg_list = nullptr; int wg_list_rows = 0;   // wgrad_tc: [1 + T*B/32] stages of the contraction holding valid rows (this batch)
   int32_t* X_rev = nullptr;   // [B, T, K] ids with every row's valid prefix reversed
   float* emb_out_rv = nullptr; float* demb_rv = nullptr;       // embedding path in reversed coordinates

@@ -895,11 +895,13 @@ static int side_fork(sbr_model* m) {
   CU_TRY(m, cudaEventRecord(m->ev_fork, m->stream));
   CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
   std::swap(m->stream, m->side);     // launchers use m->stream
+  m->on_side = true;
   return 0;
 }
 static int side_return(sbr_model* m) {   // back to the main stream; the side work keeps running
   if (m->no_side_stream) return 0;
   std::swap(m->stream, m->side);
+  m->on_side = false;
   return 0;
 }
 static int side_join(sbr_model* m) {
@@ -932,11 +934,13 @@ static int launch_deferred_output_grads(sbr_model* m) {
   if (side) {
     CU_TRY(m, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
     std::swap(m->stream, m->side);
+    m->on_side = true;
   }
   int rc = launch_gemm(m, true, false, N, H, B, m->logits, (int)round_up(N, 4), m->h_last, H, m->grads + m->out_WT, H, 1.f, 1.f);
   if (!rc) rc = launch_colsum(m, m->logits, B, N, (int)round_up(N, 4), m->grads + m->out_b);
   if (side) {
     std::swap(m->stream, m->side);
+    m->on_side = false;
     m->side_pending = true;
   }
   return rc;

@@ -456,6 +456,16 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
 
   // ======================================================================================= epilogue (thread = row)
   if (warp < 4) {
+    // bias of this thread's output columns, fetched before the accumulators are waited for (EPI_STORE: pass p, columns
+    // n0 + 32 p + 4 (lane & 7) ..)
+    float bias_pre[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = n0 + 32 * p + (lane & 7) * 4 + e;
+        bias_pre[p][e] = (EPI == EPI_STORE && a.bias && blockIdx.z == 0 && 32 * p < BN && col < a.N) ? __ldg(a.bias + col) : 0.f;
+      }
     if (n_chunks > 0) {
       mbar_wait(&done, 0);
       tc_fence_after();
@@ -499,11 +509,15 @@ __global__ void __launch_bounds__(TG_NT, 1) tc_gemm_kernel(const __grid_constant
         __syncwarp();
         const int col = n0 + c0 + c4;
         const bool col_in = col < a.N && c0 + c4 < BN;
-        float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (a.bias && blockIdx.z == 0 && col_in) {
+        float bias4[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (col + e < a.N) bias4[e] = __ldg(a.bias + col + e);
-        }
+        for (int e = 0; e < 4; ++e) bias4[e] = bias_pre[0][e];
+#pragma unroll
+        for (int p = 1; p < 4; ++p)
+          if (c0 == 32 * p) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) bias4[e] = bias_pre[p][e];
+          }
 #pragma unroll
         for (int rr = 0; rr < 32; rr += 4) {
           const int grow = m0 + warp * 32 + rr + r_in;
@@ -748,6 +762,10 @@ int launch_gemm_tc(sbr_model* m, bool ta, bool tb, int M, int N, int K, const fl
   a.B = B; a.ldb = ldb; a.b_mode = tb ? 0 : 1;
   a.M = M; a.N = N; a.K = K;
   a.BN = N <= 16 ? 16 : (N <= 32 ? 32 : (N <= 64 ? 64 : 128));
+  // small outputs (the C2 score matrix is 29 tiles of 128 columns on 148 SMs): 64-column tiles halve the B conversion and
+  // the epilogue of every CTA and double the CTAs
+  // (not for side-stream work: it runs beside a cluster scan that needs whole GPCs free, fewer and fatter CTAs interfere less)
+  if (a.BN == 128 && K <= 512 && !m->on_side && cdiv(M, 128) * cdiv(N, 128) * 2 <= m->n_sm) a.BN = 64;   // short K only: with a long K the A tile would be converted twice as often
   a.a_vec = (!ta && lda % 4 == 0 && aligned16(A)) ? 1 : 0;
   a.b_vec = (tb && ldb % 4 == 0 && aligned16(B)) ? 1 : 0;
   a.C = C; a.ldc = ldc; a.alpha = alpha; a.accumulate = beta == 1.f ? 1 : 0; a.bias = bias;
@@ -759,7 +777,7 @@ int launch_gemm_tc(sbr_model* m, bool ta, bool tb, int M, int N, int K, const fl
   }
   const int tiles = cdiv(M, 128) * cdiv(N, a.BN);
   int splits = 1;
-  if (tiles < m->n_sm) splits = std::max(1, std::min(m->n_sm / tiles, K / 256));   // tall-K, small output: fill the SMs
+  if (tiles < m->n_sm) splits = std::max(1, std::min(m->n_sm / tiles, K / 128));   // tall-K, small output: fill the SMs
   int kps = (int)round_up(cdiv(K, splits), TG_KC);
   splits = cdiv(K, kps);
   a.k_per_split = kps;

@@ -178,6 +178,14 @@ def test_embedding_path(cell):
     check_grads(spec, B=10, T=7, seed=2)
 
 
+@pytest.mark.parametrize("cell,H,K", [("GRU", 100, 1), ("LSTM", 48, 2)])
+def test_tma_staged_gather(cell, H, K, monkeypatch):
+    """SBR_GATHER_TMA=1: stage 1 through cp.async.bulk row copies into a shared-memory ring (one table row per id)."""
+    monkeypatch.setenv("SBR_GATHER_TMA", "1")
+    spec = O.Spec(n_items=211, cell=cell, layers=(H,), loss="CCE", n_extra_ids=10 if K == 2 else 0, ids_per_step=K)
+    check_grads(spec, B=11, T=9, K=K)
+
+
 def test_rating_feature_ids():
     spec = O.Spec(n_items=90, cell="GRU", layers=(32,), n_extra_ids=10, ids_per_step=2, loss="CCE")
     check_grads(spec, B=10, T=7, seed=3, K=2)
