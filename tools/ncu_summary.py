@@ -36,7 +36,10 @@ def main(rep, out):
         for k, (name, scale) in WANT.items():
             if name not in col or r[col[name]] == "":
                 continue
-            v = float(r[col[name]].replace(",", ""))
+            try:
+                v = float(r[col[name]].replace(",", ""))
+            except ValueError:          # "no data" (a metric the pass did not collect for this launch)
+                continue
             u = units[col[name]]
             if scale is None:
                 v *= UNIT_SCALE.get(u, 1)
@@ -47,7 +50,10 @@ def main(rep, out):
         for h, i in col.items():
             m = re.match(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active\.ratio|smsp__average_warp_latency_issue_stalled_(\w+)\.ratio", h)
             if m and r[i] != "":
-                stalls.append((float(r[i].replace(",", "")), m.group(1) or m.group(2)))
+                try:
+                    stalls.append((float(r[i].replace(",", "")), m.group(1) or m.group(2)))
+                except ValueError:
+                    pass
         stalls.sort(reverse=True)
         e["top_stalls"] = [{"reason": n, "ratio": round(v, 2)} for v, n in stalls[:5]]
         res.append(e)
