@@ -30,7 +30,8 @@ def _predictor(dataset, cls=None, **kw):
     from sbr_b200.neural_networks.rnn_one_hot import RNNOneHot
     from sbr_b200.neural_networks.update_manager import Adam
     cls = cls or RNNOneHot
-    p = cls(recurrent_layer=RecurrentLayers(layer_type=kw.pop("cell", "GRU"), layers=kw.pop("layers", [100])),
+    p = cls(recurrent_layer=RecurrentLayers(layer_type=kw.pop("cell", "GRU"), layers=kw.pop("layers", [100]),
+                                            bidirectional=kw.pop("bidirectional", False), embedding_size=kw.pop("emb", 0)),
             updater=Adam(), max_length=20, batch_size=16, use_ratings_features=kw.pop("rf", False),
             use_movies_features=False, use_users_features=False, **kw)
     p.prepare_model(dataset)
@@ -68,6 +69,46 @@ def test_public_api_matches_oracle_per_step_loss_and_recall(dataset):
     seq, user = next(dataset.test_set(epochs=1))
     rec = p.top_k_recommendations(seq[:len(seq) // 2], k=10)
     assert len(rec) == 10 and not set(rec) & set(seq[:len(seq) // 2, 0].astype(int))
+    p.engine.close()
+
+
+def test_a_fresh_predictor_is_initialised_and_learns(dataset):
+    """A predictor straight from the constructor has Lasagne's initial weights (not the zero arena): one training step
+    gives non-zero gradients for the recurrent and the output weights, and a few hundred steps beat the cost of the
+    first one."""
+    p = _predictor(dataset, cell="LSTM", layers=[50])
+    p._compile_train_function()
+    vals = dict(zip([n for n, _ in p.engine.param_infos()], p.engine.get_all_param_values()))
+    assert vals["l0.W_hid_to_ingate"].std() == pytest.approx(0.1, rel=0.2) and np.abs(vals["out.W"]).max() > 0
+    random.seed(5); np.random.seed(5)
+    gen = p._gen_mini_batch(dataset.training_set())
+    p.engine.set_skip_update(True)
+    p.train_function(*next(gen))
+    grads = dict(zip([n for n, _ in p.engine.param_infos()], p.engine.get_all_grads()))
+    assert np.abs(grads["l0.W_hid_to_ingate"]).max() > 0 and np.abs(grads["out.W"]).max() > 0
+    p.engine.set_skip_update(False)
+    costs = [float(p.train_function(*next(gen))) for _ in range(300)]
+    assert np.mean(costs[-20:]) < np.mean(costs[:20])
+    p.engine.close()
+
+
+@pytest.mark.parametrize("cell,layers,emb", [("GRU", [24, 16], 0), ("Vanilla", [32, 16], 0), ("LSTM", [24], 8)])
+def test_bidirectional_and_stacked_predictors_match_the_oracle(dataset, cell, layers, emb):
+    """--r_bi / --r_l a-b / --r_emb through the public API: per-step loss of the first Adam steps against the oracle."""
+    p = _predictor(dataset, cell=cell, layers=list(layers), bidirectional=True, emb=emb)
+    p._compile_train_function()
+    spec = O.Spec(n_items=500, cell=cell, layers=tuple(layers), loss="CCE", bidirectional=True, embedding=emb)
+    assert [n for n, _ in p.engine.param_infos()] == [n for n, _ in O.param_names_shapes(spec)]
+    vals = [v.astype(np.float64) for v in p.engine.get_all_param_values()]      # the predictor's own initial weights
+    upd = O.Updater("adam", lr=1e-3)
+    random.seed(99); np.random.seed(99)
+    gen = p._gen_mini_batch(dataset.training_set())
+    for step in range(8):
+        batch = next(gen)
+        c = p.train_function(*batch)
+        X, mask, Y, pop, _ = batch
+        c_ref = O.train_step(spec, vals, upd, X, mask, Y=Y, pop=pop.astype(np.float64))
+        assert abs(float(c) - float(c_ref)) < 1e-4, (step, c, c_ref)
     p.engine.close()
 
 
