@@ -487,9 +487,21 @@ def main():
                                  "peak per algorithmic FLOP",
                          "valid_steps_per_launch": mean_V, "stage_ms_all": {k: round(v, 4) for k, v in acc.items()}})
 
+    # every rank's own scan time and valid (row, step) pairs of its slice (rows r = rank mod N): the straggler is visible
+    per_rank = None
+    if ctl:
+        try:
+            my_valid = float(np.mean([np.asarray(b[1])[rank::n_gpus].sum() for b in batches[W:W + K]]))
+        except Exception:
+            my_valid = None
+        per_rank = ctl.all_gather({"rank": rank, "scan_ms": round(acc.get("rnn_fwd", 0.0) + acc.get("rnn_bwd", 0.0), 4),
+                                   "all_stages_ms": round(sum(acc.values()), 4), "valid_steps": my_valid})
+
     out = None
     if rank == 0:
         out = dict(base)
+        if per_rank is not None:
+            out["per_rank"] = sorted(per_rank, key=lambda e: e["rank"])
         out.update({"impl": "b200", "value": value, "ms_per_step": ms / K, "repeats": R, "timed_steps_total": K * R,
                     "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
                     "valid_steps_per_s": mean_V * n_gpus * K / (ms * 1e-3),
