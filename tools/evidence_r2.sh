@@ -23,3 +23,10 @@ SBR_SCAN_NO_COOP=1 timeout 900 ncu --set full --clock-control none --import-sour
     python bench.py --config c3 --steps 2 --warmup 3 --no-cpu-baseline --min-timed-s 0 > /dev/null 2> gpurun_out/r2f_ncu4.err
 ls -la gpurun_out/ | grep r2f
 for f in gpurun_out/r2f_bench_c2.json gpurun_out/r2f_bench_c2_steps20.json gpurun_out/r2f_bench_c2_no_side_stream.json gpurun_out/r2f_ref_c2.json gpurun_out/r2f_bench_c3.json gpurun_out/r2f_bench_c4_shard.json gpurun_out/r2f_bench_c5_shard.json; do echo $f; cut -c1-1400 $f; done
+
+# Multi-GPU lines of the round (each launched through `gpurun --gpus N`):
+#   N=2: python -m pytest tests/test_gpu_e2e.py -k "two_rank or nccl"; torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline
+#   N=4: torchrun --nproc-per-node 4 bench.py --gpus 4 [--config c4 --steps 8 --warmup 3] --no-cpu-baseline
+#   N=8: torchrun --nproc-per-node 8 bench.py --gpus 8 [--config c5 --steps 5 --warmup 3] --no-cpu-baseline
+#        (with NCCL_DEBUG=INFO for the NVLS line kept in profiles/r2f_nccl_info_8gpu.txt; NCCL prints to stdout)
+# with torchrun = python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port <P>
