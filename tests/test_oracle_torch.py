@@ -232,3 +232,110 @@ def test_updaters_match_an_independent_implementation(kind):
             acc = acc + g * g if kind == "adagrad" else rho * acc + (1 - rho) * g * g
             q = q - lr * g / np.sqrt(acc + 1e-6)
         np.testing.assert_allclose(p[0], q, rtol=1e-12, atol=1e-12)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Bidirectional stacks against torch.nn.GRU / torch.nn.LSTM over packed sequences: an implementation that shares
+# nothing with the oracle's go-backwards scan pins what `--r_bi` means on right-padded rows (recurrent_layers.py:72-78,
+# Lasagne `backwards=True` + mask): per depth [forward | backward] features, final state = forward state after the
+# last item | backward state after the first item.
+# --------------------------------------------------------------------------------------------------------------
+def _torch_rnn_from_oracle(spec, P):
+    """torch module carrying the oracle's weights.  GRU: torch's z gate is 1 - update gate (negated weights), its
+    candidate bias inside the reset product is zero; LSTM: no peepholes (the test zeroes them)."""
+    H_list, nd = spec.layers, 2
+    mods = []
+    n_in = spec.n_in
+    for li, H in enumerate(H_list):
+        cls = torch.nn.GRU if spec.cell == "GRU" else torch.nn.LSTM
+        m = cls(n_in, H, num_layers=1, batch_first=True, bidirectional=True).double()
+        for d, pre in enumerate(O.layer_prefixes(spec, li)):
+            sfx = "_reverse" if d else ""
+            g = lambda name: torch.tensor(P[pre + name])
+            if spec.cell == "GRU":
+                w_ih = torch.cat([g("W_in_to_resetgate"), -g("W_in_to_updategate"), g("W_in_to_hidden_update")], 1).T
+                w_hh = torch.cat([g("W_hid_to_resetgate"), -g("W_hid_to_updategate"), g("W_hid_to_hidden_update")], 1).T
+                b_ih = torch.cat([g("b_resetgate"), -g("b_updategate"), g("b_hidden_update")])
+            else:
+                names = ["ingate", "forgetgate", "cell", "outgate"]
+                w_ih = torch.cat([g("W_in_to_" + n) for n in names], 1).T
+                w_hh = torch.cat([g("W_hid_to_" + n) for n in names], 1).T
+                b_ih = torch.cat([g("b_" + n) for n in names])
+            with torch.no_grad():
+                getattr(m, "weight_ih_l0" + sfx).copy_(w_ih)
+                getattr(m, "weight_hh_l0" + sfx).copy_(w_hh)
+                getattr(m, "bias_ih_l0" + sfx).copy_(b_ih)
+                getattr(m, "bias_hh_l0" + sfx).zero_()
+        mods.append(m)
+        n_in = nd * H
+    return mods
+
+
+@pytest.mark.parametrize("cell,layers", [("GRU", (5,)), ("LSTM", (4,)), ("GRU", (4, 3)), ("LSTM", (3, 4))])
+def test_bidirectional_stack_matches_torch_packed_rnn(cell, layers):
+    rng = np.random.RandomState(21)
+    spec = O.Spec(n_items=13, cell=cell, layers=layers, loss="CCE", bidirectional=True)
+    vals = O.init_params(spec, rng)
+    for (name, _), v in zip(O.param_names_shapes(spec), vals):
+        if "W_cell_to" in name:
+            v[...] = 0.0                                  # torch's LSTM has no peepholes
+        elif not v.any():
+            v[...] = rng.normal(0, 0.2, size=v.shape)     # learned initial states and biases away from zero
+    P = O.as_dict(spec, vals)
+    X, mask, lens = make_batch(rng, 6, 7, 13)
+    lens = np.maximum(lens, 1)
+    mask = (np.arange(7)[None, :] < lens[:, None]).astype(np.float64)
+    h_last, _ = O.forward_stack(spec, P, X, mask)
+
+    mods = _torch_rnn_from_oracle(spec, P)
+    B = X.shape[0]
+    inp = torch.nn.functional.one_hot(torch.tensor(X[:, :, 0]).long(), spec.n_in).double()
+    for li, m in enumerate(mods):
+        H = spec.layers[li]
+        pres = O.layer_prefixes(spec, li)
+        h0 = torch.stack([torch.tensor(P[p + "hid_init"]).expand(B, H) for p in pres]).contiguous()
+        packed = torch.nn.utils.rnn.pack_padded_sequence(inp, torch.tensor(lens), batch_first=True, enforce_sorted=False)
+        if cell == "LSTM":
+            c0 = torch.stack([torch.tensor(P[p + "cell_init"]).expand(B, H) for p in pres]).contiguous()
+            out, (hn, _) = m(packed, (h0, c0))
+        else:
+            out, hn = m(packed, h0)
+        inp, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=X.shape[1])
+    ref = torch.cat([hn[0], hn[1]], dim=1).detach().numpy()
+    np.testing.assert_allclose(h_last, ref, rtol=0, atol=1e-10)
+
+
+def test_stacked_vanilla_matches_torch_rnn_tanh_then_relu():
+    """A Vanilla stack mixes the in-tree tanh layer (layer 0, sparse input, sparse_lstm.py:960-961) and Lasagne's
+    RecurrentLayer (rectifier) above it (recurrent_layers.py:98-99): torch.nn.RNN('tanh') feeding torch.nn.RNN('relu')."""
+    rng = np.random.RandomState(22)
+    spec = O.Spec(n_items=11, cell="Vanilla", layers=(5, 4), loss="CCE")
+    vals = O.init_params(spec, rng)
+    for v in vals:
+        if not v.any():
+            v[...] = rng.normal(0, 0.2, size=v.shape)
+        elif np.abs(v).max() <= 0.011:
+            v[...] = rng.normal(0, 0.3, size=v.shape)     # Uniform(-0.01, 0.01) would leave the rectifier barely exercised
+    P = O.as_dict(spec, vals)
+    X, mask, lens = make_batch(rng, 5, 6, 11)
+    lens = np.maximum(lens, 1)
+    mask = (np.arange(6)[None, :] < lens[:, None]).astype(np.float64)
+    h_last, _ = O.forward_stack(spec, P, X, mask)
+    B = X.shape[0]
+    inp = torch.nn.functional.one_hot(torch.tensor(X[:, :, 0]).long(), spec.n_in).double()
+    layer_params = [("l0.W_in_to_hidden_update", "l0.W_hid_to_hidden_update", "l0.b_hidden_update", "l0.hid_init", "tanh"),
+                    ("l1.W_in_to_hid", "l1.W_hid_to_hid", "l1.b", "l1.hid_init", "relu")]
+    n_in = spec.n_in
+    for (w_in, w_hid, b, h_init, nl), H in zip(layer_params, spec.layers):
+        m = torch.nn.RNN(n_in, H, nonlinearity=nl, batch_first=True).double()
+        with torch.no_grad():
+            m.weight_ih_l0.copy_(torch.tensor(P[w_in]).T)
+            m.weight_hh_l0.copy_(torch.tensor(P[w_hid]).T)
+            m.bias_ih_l0.copy_(torch.tensor(P[b]))
+            m.bias_hh_l0.zero_()
+        packed = torch.nn.utils.rnn.pack_padded_sequence(inp, torch.tensor(lens), batch_first=True, enforce_sorted=False)
+        out, hn = m(packed, torch.tensor(P[h_init]).expand(B, H).unsqueeze(0).contiguous())
+        inp, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=X.shape[1])
+        n_in = H
+    np.testing.assert_allclose(h_last, hn[0].detach().numpy(), rtol=0, atol=1e-10)
+    assert (h_last == 0).any() and (h_last > 0).any()          # the rectifier really clips some units
