@@ -21,7 +21,12 @@ One JSON line on stdout (rank 0):
   roofline   the dominant kernel (largest stage of the step), algorithmic FLOPs / its measured
              launch time, against MEASURED_PEAKS.json;
   cpu_baseline  the numpy restatement of the reference's Theano CPU path (oracle/, "port") timed on
-             this box's host cores on a bounded sample of the same batches (rank 0, N=1 only).
+             this box's host cores on a bounded sample of the same batches (rank 0, N=1 only);
+  valid_steps_per_s  valid (row, step) pairs per second over all ranks: the global batches of N ranks hold longer
+             rows, this number separates that workload shift from overhead in a scaling curve;
+  per_rank   (N > 1) every rank's scan time and the valid steps of its slice -- a straggler is visible;
+  multi_rank_cost_check  (N > 1, C1/C2) the all-reduced global cost of step 0 against a one-rank replay of the same
+             global batch; parity / parity_max_abs (N = 1) the step-0 cost against the CPU port.
 
 `--impl reference` times that CPU restatement alone (the reference itself -- Python 2 + Theano +
 Lasagne -- cannot be installed here) with all host threads numpy's BLAS will use.
