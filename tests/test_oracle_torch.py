@@ -339,3 +339,75 @@ def test_stacked_vanilla_matches_torch_rnn_tanh_then_relu():
         n_in = H
     np.testing.assert_allclose(h_last, hn[0].detach().numpy(), rtol=0, atol=1e-10)
     assert (h_last == 0).any() and (h_last > 0).any()          # the rectifier really clips some units
+
+
+@pytest.mark.parametrize("cell,layers", [("GRU", (4, 3)), ("LSTM", (3,))])
+def test_bidirectional_gradients_match_torch_packed_rnn(cell, layers):
+    """Cost and every recurrent / output gradient of a bidirectional CCE step against torch.autograd through
+    torch.nn.GRU / LSTM over packed sequences (grad_clip far away; peepholes zero for the LSTM)."""
+    rng = np.random.RandomState(23)
+    spec = O.Spec(n_items=11, cell=cell, layers=layers, loss="CCE", bidirectional=True, grad_clip=1e6)
+    vals = O.init_params(spec, rng)
+    for (name, _), v in zip(O.param_names_shapes(spec), vals):
+        if "W_cell_to" in name:
+            v[...] = 0.0
+        elif not v.any():
+            v[...] = rng.normal(0, 0.2, size=v.shape)
+    P = O.as_dict(spec, vals)
+    X, mask, lens = make_batch(rng, 5, 6, 11)
+    lens = np.maximum(lens, 1)
+    mask = (np.arange(6)[None, :] < lens[:, None]).astype(np.float64)
+    B = X.shape[0]
+    Y = rng.randint(0, 11, B)
+    pop = rng.uniform(0.5, 2.0, B)
+    cost, grads = O.loss_and_grads(spec, vals, X, mask, Y=Y, pop=pop)
+    G = dict(zip([n for n, _ in O.param_names_shapes(spec)], grads))
+
+    mods = _torch_rnn_from_oracle(spec, P)
+    for m in mods:
+        for p_ in m.parameters():
+            p_.requires_grad_(True)
+    W_out = torch.tensor(P["out.W"], requires_grad=True)
+    b_out = torch.tensor(P["out.b"], requires_grad=True)
+    inits = {}
+    inp = torch.nn.functional.one_hot(torch.tensor(X[:, :, 0]).long(), spec.n_in).double()
+    for li, m in enumerate(mods):
+        H = spec.layers[li]
+        pres = O.layer_prefixes(spec, li)
+        for p_ in pres:
+            inits[p_ + "hid_init"] = torch.tensor(P[p_ + "hid_init"], requires_grad=True)
+            if cell == "LSTM":
+                inits[p_ + "cell_init"] = torch.tensor(P[p_ + "cell_init"], requires_grad=True)
+        h0 = torch.stack([inits[p_ + "hid_init"].expand(B, H) for p_ in pres]).contiguous()
+        packed = torch.nn.utils.rnn.pack_padded_sequence(inp, torch.tensor(lens), batch_first=True, enforce_sorted=False)
+        if cell == "LSTM":
+            c0 = torch.stack([inits[p_ + "cell_init"].expand(B, H) for p_ in pres]).contiguous()
+            out, (hn, _) = m(packed, (h0, c0))
+        else:
+            out, hn = m(packed, h0)
+        inp, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=X.shape[1])
+    h = torch.cat([hn[0], hn[1]], dim=1)
+    logp = torch.log_softmax(h @ W_out + b_out, dim=1)
+    tcost = (-logp[torch.arange(B), torch.tensor(Y).long()] / torch.tensor(pop)).mean()
+    tcost.backward()
+    assert abs(tcost.item() - cost) < 1e-10
+    np.testing.assert_allclose(G["out.W"], W_out.grad.numpy(), atol=1e-9)
+    np.testing.assert_allclose(G["out.b"], b_out.grad.numpy(), atol=1e-9)
+    for li, m in enumerate(mods):
+        H = spec.layers[li]
+        for d, pre in enumerate(O.layer_prefixes(spec, li)):
+            sfx = "_reverse" if d else ""
+            g_hh = getattr(m, "weight_hh_l0" + sfx).grad.numpy().T          # [H, G*H], torch gate order
+            g_ih = getattr(m, "weight_ih_l0" + sfx).grad.numpy().T
+            g_b = getattr(m, "bias_ih_l0" + sfx).grad.numpy()
+            if cell == "GRU":
+                names, signs = ["resetgate", "updategate", "hidden_update"], [1.0, -1.0, 1.0]
+            else:
+                names, signs = ["ingate", "forgetgate", "cell", "outgate"], [1.0, 1.0, 1.0, 1.0]
+            for gi, (n, sg) in enumerate(zip(names, signs)):
+                np.testing.assert_allclose(G[pre + "W_hid_to_" + n], sg * g_hh[:, gi * H:(gi + 1) * H], atol=1e-9, err_msg=pre + n)
+                np.testing.assert_allclose(G[pre + "W_in_to_" + n], sg * g_ih[:, gi * H:(gi + 1) * H], atol=1e-9, err_msg=pre + n)
+                np.testing.assert_allclose(G[pre + "b_" + n], sg * g_b[gi * H:(gi + 1) * H], atol=1e-9, err_msg=pre + n)
+            np.testing.assert_allclose(G[pre + "hid_init"], inits[pre + "hid_init"].grad.numpy(), atol=1e-9)
+            if cell == "LSTM":
+                np.testing.assert_allclose(G[pre + "cell_init"], inits[pre + "cell_init"].grad.numpy(), atol=1e-9)
