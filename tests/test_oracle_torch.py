@@ -411,3 +411,46 @@ def test_bidirectional_gradients_match_torch_packed_rnn(cell, layers):
             np.testing.assert_allclose(G[pre + "hid_init"], inits[pre + "hid_init"].grad.numpy(), atol=1e-9)
             if cell == "LSTM":
                 np.testing.assert_allclose(G[pre + "cell_init"], inits[pre + "cell_init"].grad.numpy(), atol=1e-9)
+
+
+def test_embedding_rating_ids_and_stack_match_torch():
+    """--r_emb with two ids per step (item + rating feature, rnn_base.py:578-593): EmbeddingLayer + flatten(outdim=3)
+    (recurrent_layers.py:47) feeding a two-layer GRU -- torch.nn.Embedding, concatenation, two torch.nn.GRU modules."""
+    rng = np.random.RandomState(24)
+    spec = O.Spec(n_items=9, cell="GRU", layers=(4, 3), loss="CCE", embedding=3, n_extra_ids=5, ids_per_step=2, grad_clip=1e6)
+    vals = O.init_params(spec, rng)
+    for v in vals:
+        if not v.any():
+            v[...] = rng.normal(0, 0.2, size=v.shape)
+    P = O.as_dict(spec, vals)
+    X, mask, lens = make_batch(rng, 5, 6, 9, 2, 5)
+    lens = np.maximum(lens, 1)
+    mask = (np.arange(6)[None, :] < lens[:, None]).astype(np.float64)
+    B, T, K = X.shape
+    Y = rng.randint(0, 9, B)
+    pop = rng.uniform(0.5, 2.0, B)
+    cost, grads = O.loss_and_grads(spec, vals, X, mask, Y=Y, pop=pop)
+    G = dict(zip([n for n, _ in O.param_names_shapes(spec)], grads))
+
+    emb = torch.tensor(P["emb.W"], requires_grad=True)
+    inp = emb[torch.tensor(X).long()].reshape(B, T, K * spec.embedding)
+    n_in = K * spec.embedding
+    hn = None
+    for li, H in enumerate(spec.layers):
+        pre = "l%d." % li
+        g = lambda name: torch.tensor(P[pre + name])
+        m = torch.nn.GRU(n_in, H, batch_first=True).double()
+        with torch.no_grad():
+            m.weight_ih_l0.copy_(torch.cat([g("W_in_to_resetgate"), -g("W_in_to_updategate"), g("W_in_to_hidden_update")], 1).T)
+            m.weight_hh_l0.copy_(torch.cat([g("W_hid_to_resetgate"), -g("W_hid_to_updategate"), g("W_hid_to_hidden_update")], 1).T)
+            m.bias_ih_l0.copy_(torch.cat([g("b_resetgate"), -g("b_updategate"), g("b_hidden_update")]))
+            m.bias_hh_l0.zero_()
+        packed = torch.nn.utils.rnn.pack_padded_sequence(inp, torch.tensor(lens), batch_first=True, enforce_sorted=False)
+        out, hn = m(packed, g("hid_init").expand(B, H).unsqueeze(0).contiguous())
+        inp, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=T)
+        n_in = H
+    logp = torch.log_softmax(hn[0] @ torch.tensor(P["out.W"]) + torch.tensor(P["out.b"]), dim=1)
+    tcost = (-logp[torch.arange(B), torch.tensor(Y).long()] / torch.tensor(pop)).mean()
+    tcost.backward()
+    assert abs(tcost.item() - cost) < 1e-10
+    np.testing.assert_allclose(G["emb.W"], emb.grad.numpy(), atol=1e-9)
