@@ -9,7 +9,10 @@ PARITY UNPINNED: the reference (rdevooght/sequence-based-recommendations @0dfefe
 no tests, golden vectors or seeds, and Theano/Lasagne cannot be installed here (Python 2
 only, no network).  The pins that exist are manufactured: (1) float64 finite-difference
 gradient checks of every cell and loss in ``tests/test_oracle.py``; (2) an independent
-``torch.autograd`` re-derivation of the same graph in ``tests/test_oracle_torch.py``;
+``torch.autograd`` re-derivation of the same graph in ``tests/test_oracle_torch.py`` (cells with the grad_clip sites,
+sampling and margin losses, updaters) and, for everything torch ships its own implementation of, torch's own modules:
+bidirectional and stacked GRU / LSTM over packed sequences (states and gradients), the tanh-then-rectifier Vanilla
+stack, the embedding + rating-id input path;
 (3) frozen fixtures under ``tests/golden/`` made by ``tests/golden/make_golden.py``.
 
 Every function cites the reference file:line it follows (paths relative to
